@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s (physics + obs + reward + done + auto-reset) of the batched sumo arena.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E_PER_GPU]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one VecEnv.step over E Ant-vs-Ant env pairs per GPU (BASELINE.json configs[1], E = 4096):
+5 substeps x RK4 = 20 forward-dynamics evaluations per pair, fused obs / reward / done / auto-reset.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_PAIR_STEP = 1530          # Ant-vs-Ant, fp32 storage
+ENV_ID = 'RoboSumo-Ant-vs-Ant-v0'
+METRIC = 'env-steps/sec (physics+obs+reward)'
+
+
+def read_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_port_rate(seconds, envs, threads):
+    """Oracle port (oracle/physics_oracle.c) stepping `envs` independent pairs with `threads` host threads for
+    about `seconds`; the env-level reward/obs arithmetic is negligible beside the physics and is not included."""
+    import numpy as np
+    from oracle.physics import OracleModel, load_model_json
+    om = OracleModel(load_model_json('ant_ant'))
+    rng = np.random.RandomState(0)
+    q = np.tile(om.qpos0, (envs, 1)); v = np.zeros((envs, om.nv)); w = np.zeros((envs, om.nv))
+    phi = rng.uniform(0, 2 * np.pi, envs)
+    for a in range(2):
+        q[:, 15 * a] = 1.15 * np.cos(phi + a * np.pi); q[:, 15 * a + 1] = 1.15 * np.sin(phi + a * np.pi); q[:, 15 * a + 2] = 1.25
+    q += rng.uniform(-.1, .1, q.shape); v += 0.1 * rng.randn(*v.shape)
+    for _ in range(3):                                       # warm-up: let the ants land
+        om.step_batch(q, v, rng.randn(envs, om.nu), 5, w, threads)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        om.step_batch(q, v, rng.randn(envs, om.nu), 5, w, threads)
+        n += envs
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return n / el, n, el
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU path.  MuJoCo 2.1 / mujoco-py cannot be installed here (closed binary,
+    no network), so this times the oracle port of the same physics on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    envs = 16 * cores
+    per_step_s = 2.0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        rate, n, el = cpu_port_rate(per_step_s, envs, cores)
+        if i >= args.warmup:
+            vals.append((rate, n, el))
+    tot_n = sum(v[1] for v in vals); tot_t = sum(v[2] for v in vals)
+    value = tot_n / tot_t
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / len(vals), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'RoboSumo-Ant-vs-Ant-v0 physics step, CPU oracle port on host cores',
+                   'envs_per_step': envs, 'frame_skip': 5, 'integrator': 'RK4'},
+        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d env pairs x ~%.0f s per step, %d steps, N(0,1) actions' % (envs, per_step_s, args.steps)},
+        'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=4096, help='env pairs per GPU')
+    ap.add_argument('--settle', type=int, default=40, help='untimed steps before warm-up so contacts exist')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-flush', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from robosumo_selfplay_b200 import _lib
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    assert args.warmup >= 3, "W >= 3 warm-up steps"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    E = args.envs
+    L = _lib.lib()
+    env = B200SumoVecEnv(ENV_ID, num_envs=E, seed=42 + rank, device=local, device_api=True)
+    env.reset()
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    pool = [torch.randn(E, 2, 8, device=dev, generator=g) for _ in range(16)]      # N(0,1) actions (untrained policy)
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for t in range(args.settle + args.warmup):
+        env.step(pool[t % 16])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.rs_launch_count()
+    stream = torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for t in range(args.steps):
+        if flush is not None:
+            flush.fill_(t & 255)                     # evict L2 between timed steps (untimed)
+        ev[t][0].record(stream)
+        env.step(pool[t % 16])
+        ev[t][1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = L.rs_launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_t.item()) / args.steps
+    clocks = sampler.summary() if rank == 0 else None
+    q, v, step, status = env.get_state()
+    ncon_note = int((status & 2).sum().item())
+
+    # ---- e2e: the public host API (numpy in / numpy out), copies inside the timed region ----
+    henv = B200SumoVecEnv(ENV_ID, num_envs=E, seed=4242 + rank, device=local, device_api=False)
+    henv.reset()
+    hact = [np.random.RandomState(7 + i).randn(E, 2, 8).astype(np.float32) for i in range(8)]
+    for t in range(args.settle // 2 + args.warmup):
+        henv.step_async(hact[t % 8]); henv.step_wait()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_e2e = max(20, args.steps // 4)
+    a32 = hact[0].reshape(E, 16)
+    t0 = time.perf_counter()
+    for t in range(n_e2e):
+        a = hact[t % 8].reshape(E, 16)
+        _lib.check(L.rs_step_host(henv._h, henv._np(a), henv._np(henv.h_obs), henv._np(henv.h_rew), henv._np(henv.h_done),
+                                  henv._np(henv.h_info), henv._np(henv.h_epi), 1))
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = E * world * n_e2e / float(e2e_t.item())
+    h2d = a32.nbytes
+    d2h = henv.h_obs.nbytes + henv.h_rew.nbytes + henv.h_done.nbytes + henv.h_info.nbytes + henv.h_epi.nbytes
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = E * world / (ms_per_step / 1e3)
+    peak, peak_src = read_peaks()
+    achieved = ALGO_BYTES_PER_PAIR_STEP * E / (ms_per_step / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'k_step_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    cores = os.cpu_count() or 1
+    cpu_rate, cpu_n, cpu_el = cpu_port_rate(args.cpu_seconds, 16 * cores, cores)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'RoboSumo-Ant-vs-Ant-v0, %d env pairs per GPU, physics(5x RK4)+obs+reward+done+auto-reset' % E,
+                   'envs_per_gpu': E, 'frame_skip': 5, 'integrator': 'RK4', 'solver': 'Newton (primal), pyramidal cone',
+                   'actions': 'N(0,1) i.i.d.', 'settle_steps': args.settle,
+                   'l2': 'flushed between timed steps (256 MiB write, untimed)' if flush is not None else 'not flushed',
+                   'timing': 'CUDA events per step on the launch stream, summed; max over ranks'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_unit': ALGO_BYTES_PER_PAIR_STEP,
+                     'note': 'state stays in shared memory for all 20 forward evaluations; the kernel is FP32-latency/'
+                             'issue bound by construction, so the HBM fraction is low (DESIGN.md)'},
+        'cpu_baseline': {'value': cpu_rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d env-steps (%d pairs, N(0,1) actions) in %.1f s on %d threads' % (cpu_n, 16 * cores, cpu_el, cores)},
+        'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'steps': n_e2e, 'api': 'rs_step_host (B200SumoVecEnv host style: numpy actions in, obs/rew/done/info out)'},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'contact_full_envs': ncon_note,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,106 @@
+/* rs_b200.h -- C ABI of the B200-native RoboSumo hot path.
+ *
+ * Drop-in boundary.  Every entry point replaces one interface of the
+ * reference; pointers are DEVICE pointers unless the name says "host"; all calls are
+ * stream-ordered on the supplied CUDA stream (a `cudaStream_t` passed as void*), return 0 on
+ * success or a negative code, and never throw.  `rs_last_error()` describes the last failure.
+ *
+ *   rs_create / rs_destroy      SubprocVecEnv.__init__/close   subproc_vec_env.py:40-63,83-93
+ *                               + gym.make(...)                 robosumo/robosumo/__init__.py:8-105
+ *                               + MujocoEnv.__init__            robosumo/robosumo/envs/mujoco_env.py:47-56
+ *   rs_reset                    SubprocVecEnv.reset             subproc_vec_env.py:78-82
+ *                               -> SumoEnv.reset_model          robosumo/robosumo/envs/sumo.py:232-253
+ *   rs_set_state / rs_get_state MujocoEnv.set_state / sim.get_state   mujoco_env.py:110-119,
+ *                               mujoco-py/mujoco_py/mjsimstate.pyx:31-39 (qpos|qvel flattening)
+ *   rs_step                     SubprocVecEnv.step_async+step_wait    subproc_vec_env.py:65-76
+ *                               -> worker auto-reset            subproc_vec_env.py:12-16
+ *                               -> sumo_env.SumoEnv.step        sumo_env.py:40-72
+ *                               -> SumoEnv._step                sumo.py:120-192
+ *                               -> do_simulation / mj_step x5   mujoco_env.py:125-129, mjsim.pyx:115-129
+ *   rs_step_host                same call with HOST numpy buffers (what a SubprocVecEnv user holds)
+ *   rs_forward_debug            sim.forward() + data.qacc / data.ncon (parity hook)  mjsim.pyx:101-106
+ *   rs_policy_*                 PolicyWithValue.step/value/action_probability   policies.py:84-128
+ *   rs_vtrace                   Runner.run V-trace block        runner.py:166-200
+ *   rs_ppo_*                    PPOModel.train                  model.py:179-213 (graph 51-139)
+ */
+#ifndef RS_B200_H
+#define RS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_MAXL 8            /* max legs per agent (spider) */
+#define RS_INFO_DIM 8        /* ctrl, lose, win, main, move, push, shaping, flags(bit0 winner, bit1 timeout) */
+
+#define RS_OK 0
+#define RS_ERR_ARG -1
+#define RS_ERR_CUDA -2
+#define RS_ERR_UNSUPPORTED -3
+
+/* status bits (per env, sticky until rs_reset): the analogue of MuJoCo warnings raised as
+ * MujocoException by mujoco-py (builder.py:351-369) */
+#define RS_STATUS_NAN 1          /* mjWARN_BADQPOS/BADQVEL/BADQACC */
+#define RS_STATUS_CONTACT_FULL 2 /* mjWARN_CONTACTFULL: more than RS_MAXCON contacts, extra ones dropped */
+#define RS_STATUS_NEWTON_MAXIT 4 /* constraint solver hit its iteration cap */
+
+/* Per-morphology constants in the layout the kernels read (built by morphology.py). */
+typedef struct rs_agent_model {
+    int L, nq, nv, nu;
+    float torso_r, leg_r, armature, damping, gear, adjust_z, reach, pad2;   /* reach: bounding radius about the torso origin */
+    float mT, cT[3], IT[9];                 /* torso rigid group: mass, com, inertia about com (torso frame) */
+    float iw_torso, iw_aux[RS_MAXL], iw_hip[RS_MAXL], iw_ank[RS_MAXL];   /* body_invweight0 (translational) */
+    float iwd_hip[RS_MAXL], iwd_ank[RS_MAXL];                             /* dof_invweight0 */
+    float r_hip[RS_MAXL][3], ax_hip[RS_MAXL][3], r_ank[RS_MAXL][3], ax_ank[RS_MAXL][3], e_ank[RS_MAXL][3];
+    float m_hip[RS_MAXL], ip_hip[RS_MAXL], ia_hip[RS_MAXL], m_ank[RS_MAXL], ip_ank[RS_MAXL], ia_ank[RS_MAXL];
+    float lo_hip[RS_MAXL], hi_hip[RS_MAXL], lo_ank[RS_MAXL], hi_ank[RS_MAXL];
+} rs_agent_model;
+
+typedef struct rs_config {
+    int num_envs;            /* env pairs on this device */
+    int frame_skip;          /* 5   (sumo.py:50) */
+    int timestep_limit;      /* 500 (robosumo/__init__.py) */
+    int newton_iters;        /* cap on Newton iterations per forward evaluation (default 8) */
+    float timestep;          /* 0.01 (tatami.xml:3) */
+    float ring_limit;        /* tatami_size + 0.1 (sumo.py:55) */
+    float init_pos_noise;    /* 0.1 */
+    float init_vel_noise;    /* 0.1 */
+    uint64_t seed;           /* Philox key; env e uses stream (seed, e) */
+    int device;
+    int reserved;
+} rs_config;
+
+typedef struct rs_env rs_env;
+
+int rs_agent_model_size(void);
+const char* rs_last_error(void);
+
+int rs_create(const rs_config* cfg, const rs_agent_model* agents /* [2], host */, rs_env** out);
+void rs_destroy(rs_env* h);
+int rs_dims(const rs_env* h, int* nq, int* nv, int* nu, int* obs_a, int* obs_b, int* act_a, int* act_b);
+
+/* mask: uint8[E] (device) or NULL = all.  obs: float[E][obs_a+obs_b] (agent 0 then agent 1). */
+int rs_reset(rs_env* h, const uint8_t* mask, float* obs, void* stream);
+int rs_set_state(rs_env* h, const float* qpos, const float* qvel, float* obs, void* stream);
+int rs_get_state(rs_env* h, float* qpos, float* qvel, int* ep_step, int* status, void* stream);
+
+/* actions: float[E][act_a+act_b]; obs as above; rew float[E][2]; done uint8[E][2];
+ * info float[E][2][RS_INFO_DIM]; episode float[E][3] = (r, dr, l) of agent 0, valid where done[e][0]. */
+int rs_step(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* done, float* info,
+            float* episode, int auto_reset, void* stream);
+/* same, HOST buffers; H2D/D2H copies happen inside (pinned staging owned by the handle) */
+int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* done, float* info,
+                 float* episode, int auto_reset);
+
+/* parity hook: one forward evaluation at the stored state with the given ctrl (device pointers):
+ * qacc float[E][nv], ncon int[E], niter int[E] */
+int rs_forward_debug(rs_env* h, const float* ctrl, float* qacc, int* ncon, int* niter, void* stream);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long rs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

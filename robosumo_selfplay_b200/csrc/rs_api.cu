@@ -1,0 +1,369 @@
+// rs_api.cu -- CUDA kernels (one warp per env pair) and the C ABI of include/rs_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <type_traits>
+#include "rs_env.h"
+#include "rs_learn.cuh"
+
+using namespace rs;
+
+#define RS_WPB 5   // warps (env pairs) per block: 5 slabs of 14.7 KB -> 3 blocks = 15 warps per SM
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches(0);
+static int fail(int code, const char* fmt, const char* detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CUDA_OK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(RS_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(_e)); } while (0)
+
+struct EnvDev {
+    int E;
+    float *qpos, *qvel, *warm, *ep_ret, *ep_dret;
+    int *ep_step, *status;
+    unsigned int* ep_count;
+    const rs_agent_model* am;
+    EnvParams P;
+    float h;
+    int max_newton;
+};
+
+struct rs_env {
+    rs_config cfg;
+    int LA, LB, nq, nv, nu, obsA, obsB;
+    EnvDev d;
+    rs_agent_model* d_am;
+    // staging for the host-buffer entry point
+    float *h_act, *h_obs, *h_rew, *h_info, *h_epi;
+    uint8_t* h_done;
+    float *s_act, *s_obs, *s_rew, *s_info, *s_epi;
+    uint8_t* s_done;
+    cudaStream_t stream;
+    size_t smem;
+};
+
+template <int LA, int LB>
+__device__ __forceinline__ Slab<LA, LB>* warp_setup(Ctx<LA, LB>& c, const EnvDev& d, rs_agent_model* sm_am, unsigned char* smem_raw) {
+    typedef Slab<LA, LB> S;
+    for (int i = threadIdx.x; i < (int)(2 * sizeof(rs_agent_model) / 4); i += blockDim.x) ((int*)sm_am)[i] = ((const int*)d.am)[i];
+    __syncthreads();
+    S* s = reinterpret_cast<S*>(smem_raw) + (threadIdx.x >> 5);
+    c.s = s; c.am = sm_am; c.h = d.h; c.max_newton = d.max_newton;
+    return s;
+}
+
+template <int LA, int LB>
+__device__ __forceinline__ void load_state(Ctx<LA, LB>& c, const EnvDev& d, int e) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NQ) { s.q[i] = d.qpos[(size_t)e * S::NQ + i]; }
+    RS_LANE_LOOP(i, S::NV) { s.v[i] = d.qvel[(size_t)e * S::NV + i]; s.x[i] = d.warm[(size_t)e * S::NV + i]; }
+    RS_LANE_LOOP(i, S::NV * S::NVP) { s.M[i] = 0.f; }
+    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; }
+    RS_SYNC();
+}
+template <int LA, int LB>
+__device__ __forceinline__ void store_state(Ctx<LA, LB>& c, const EnvDev& d, int e) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NQ) { d.qpos[(size_t)e * S::NQ + i] = s.q[i]; }
+    RS_LANE_LOOP(i, S::NV) { d.qvel[(size_t)e * S::NV + i] = s.v[i]; d.warm[(size_t)e * S::NV + i] = s.x[i]; }
+}
+template <int LA, int LB>
+__device__ __forceinline__ void set_act(Ctx<LA, LB>& c, const float* ctrl) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(u, S::NU) {
+        float x = ctrl[u];
+        x = fminf(fmaxf(x, -1.f), 1.f);                       // ctrllimited, ctrlrange +-1
+        s.act[u] = c.am[u >= 2 * LA ? 1 : 0].gear * x;
+    }
+    RS_SYNC();
+}
+__device__ __forceinline__ float tsfeat(int step) { return (float)(-1.0 + 2.0 * (double)step / 500.0); }
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(32 * RS_WPB) k_reset(EnvDev d, const uint8_t* mask, float* obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ rs_agent_model sm_am[2];
+    typedef Slab<LA, LB> S;
+    Ctx<LA, LB> c;
+    warp_setup(c, d, sm_am, smem_raw);
+    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    if (e >= d.E) return;
+    if (mask && !mask[e]) return;
+    S& s = *c.s;
+    unsigned int ep = d.ep_count[e] + 1;
+    env_reset_state(c, d.P, (uint32_t)e, ep);
+    store_state(c, d, e);
+    if (RS_LANE0) { d.ep_count[e] = ep; d.ep_step[e] = 0; d.ep_ret[e] = 0.f; d.ep_dret[e] = 0.f; d.status[e] = 0; }
+    const int OD = (7 + 2*LA) + (6 + 2*LA) + 6 * (1 + 3*LA) + 14 + (7 + 2*LB) + (6 + 2*LB) + 6 * (1 + 3*LB) + 14;
+    if (obs) env_write_obs(c, obs + (size_t)e * OD, -1.f);
+    (void)s;
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(32 * RS_WPB) k_set_state(EnvDev d, const float* qpos, const float* qvel, float* obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ rs_agent_model sm_am[2];
+    typedef Slab<LA, LB> S;
+    Ctx<LA, LB> c;
+    warp_setup(c, d, sm_am, smem_raw);
+    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    if (e >= d.E) return;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NQ) { s.q[i] = qpos[(size_t)e * S::NQ + i]; }
+    RS_LANE_LOOP(i, S::NV) { s.v[i] = qvel[(size_t)e * S::NV + i]; s.x[i] = 0.f; }
+    RS_SYNC();
+    RS_LANE_LOOP(a, 2) {
+        float* qq = s.q + c.qadr(a);
+        float n = sqrtf(qq[3]*qq[3] + qq[4]*qq[4] + qq[5]*qq[5] + qq[6]*qq[6]);
+        float inv = n > 1e-12f ? 1.f / n : 1.f;
+        qq[3] *= inv; qq[4] *= inv; qq[5] *= inv; qq[6] *= inv;
+    }
+    RS_SYNC();
+    store_state(c, d, e);
+    if (RS_LANE0) d.status[e] = 0;
+    const int OD = (7 + 2*LA) + (6 + 2*LA) + 6 * (1 + 3*LA) + 14 + (7 + 2*LB) + (6 + 2*LB) + 6 * (1 + 3*LB) + 14;
+    if (obs) env_write_obs(c, obs + (size_t)e * OD, tsfeat(d.ep_step[e]));
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __restrict__ actions, float* __restrict__ obs,
+                                                       float* __restrict__ rew, uint8_t* __restrict__ done,
+                                                       float* __restrict__ info, float* __restrict__ episode, int auto_reset) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ rs_agent_model sm_am[2];
+    typedef Slab<LA, LB> S;
+    Ctx<LA, LB> c;
+    warp_setup(c, d, sm_am, smem_raw);
+    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    if (e >= d.E) return;
+    S& s = *c.s;
+    const int lane = threadIdx.x & 31;
+    load_state(c, d, e);
+    const float* act = actions + (size_t)e * S::NU;
+    set_act(c, act);
+    float before[4] = { s.q[c.qadr(0)], s.q[c.qadr(0) + 1], s.q[c.qadr(1)], s.q[c.qadr(1) + 1] };
+    RS_SYNC();
+    simulate(c, d.P.frame_skip);
+    // mj_checkPos / mj_checkVel analogue
+    {
+        bool bad = false;
+        RS_LANE_LOOP(i, S::NQ) { if (!isfinite(s.q[i])) bad = true; }
+        RS_LANE_LOOP(i, S::NV) { if (!isfinite(s.v[i])) bad = true; }
+        if (__any_sync(0xffffffffu, bad)) { if (lane == 0) s.status |= RS_STATUS_NAN; }
+        RS_SYNC();
+    }
+    int num_steps = d.ep_step[e] + 1;
+    StepOut o;
+    env_rewards(c, d.P, before, act, num_steps, d.h * d.P.frame_skip, &o);
+    float er = d.ep_ret[e] + o.rew[0], edr = d.ep_dret[e] + o.info[0][6];
+    if (lane == 0) {
+        rew[2 * e] = o.rew[0]; rew[2 * e + 1] = o.rew[1];
+        done[2 * e] = (uint8_t)o.done[0]; done[2 * e + 1] = (uint8_t)o.done[1];
+        if (episode) { episode[3 * e] = er; episode[3 * e + 1] = edr; episode[3 * e + 2] = (float)num_steps; }
+    }
+    if (info && lane < 2 * RS_INFO_DIM) info[(size_t)e * 2 * RS_INFO_DIM + lane] = o.info[lane / RS_INFO_DIM][lane % RS_INFO_DIM];
+    const int OD = (7 + 2*LA) + (6 + 2*LA) + 6 * (1 + 3*LA) + 14 + (7 + 2*LB) + (6 + 2*LB) + 6 * (1 + 3*LB) + 14;
+    RS_SYNC();
+    int st = s.status;
+    if (o.done[0] && auto_reset) {
+        unsigned int ep = d.ep_count[e] + 1;
+        env_reset_state(c, d.P, (uint32_t)e, ep);
+        store_state(c, d, e);
+        if (lane == 0) { d.ep_count[e] = ep; d.ep_step[e] = 0; d.ep_ret[e] = 0.f; d.ep_dret[e] = 0.f; d.status[e] = st & RS_STATUS_CONTACT_FULL; }
+        env_write_obs(c, obs + (size_t)e * OD, -1.f);
+    } else {
+        store_state(c, d, e);
+        if (lane == 0) { d.ep_step[e] = num_steps; d.ep_ret[e] = er; d.ep_dret[e] = edr; d.status[e] = st | (o.done[0] ? 8 : 0); }
+        env_write_obs(c, obs + (size_t)e * OD, tsfeat(num_steps));
+    }
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(32 * RS_WPB) k_forward_debug(EnvDev d, const float* ctrl, float* qacc, int* ncon, int* niter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ rs_agent_model sm_am[2];
+    typedef Slab<LA, LB> S;
+    Ctx<LA, LB> c;
+    warp_setup(c, d, sm_am, smem_raw);
+    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    if (e >= d.E) return;
+    S& s = *c.s;
+    load_state(c, d, e);
+    set_act(c, ctrl + (size_t)e * S::NU);
+    forward(c);
+    RS_LANE_LOOP(i, S::NV) { qacc[(size_t)e * S::NV + i] = s.x[i]; }
+    if (RS_LANE0) { ncon[e] = s.ncon; niter[e] = s.niter; }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <typename F> static int dispatch(const rs_env* h, F f) {
+    if (h->LA == 4 && h->LB == 4) return f(std::integral_constant<int, 4>(), std::integral_constant<int, 4>());
+    if (h->LA == 6 && h->LB == 6) return f(std::integral_constant<int, 6>(), std::integral_constant<int, 6>());
+    if (h->LA == 8 && h->LB == 8) return f(std::integral_constant<int, 8>(), std::integral_constant<int, 8>());
+    return fail(RS_ERR_UNSUPPORTED, "unsupported morphology pair (%s)", "legs");
+}
+static size_t slab_bytes(int LA, int LB) {
+    if (LA == 4 && LB == 4) return sizeof(Slab<4, 4>);
+    if (LA == 6 && LB == 6) return sizeof(Slab<6, 6>);
+    if (LA == 8 && LB == 8) return sizeof(Slab<8, 8>);
+    return 0;
+}
+
+extern "C" {
+
+int rs_agent_model_size(void) { return (int)sizeof(rs_agent_model); }
+const char* rs_last_error(void) { return g_err; }
+long long rs_launch_count(void) { return g_launches.load(); }
+
+int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) {
+    if (!cfg || !agents || !out || cfg->num_envs <= 0) return fail(RS_ERR_ARG, "rs_create: bad argument%s", "");
+    CUDA_OK(cudaSetDevice(cfg->device));
+    rs_env* h = new rs_env();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->LA = agents[0].L; h->LB = agents[1].L;
+    h->nq = agents[0].nq + agents[1].nq; h->nv = agents[0].nv + agents[1].nv; h->nu = agents[0].nu + agents[1].nu;
+    h->obsA = agents[0].nq + agents[0].nv + 6 * (1 + 3 * agents[0].L) + 14;
+    h->obsB = agents[1].nq + agents[1].nv + 6 * (1 + 3 * agents[1].L) + 14;
+    size_t sb = slab_bytes(h->LA, h->LB);
+    if (!sb) { delete h; return fail(RS_ERR_UNSUPPORTED, "unsupported morphology pair%s", ""); }
+    h->smem = sb * RS_WPB;
+    const int E = cfg->num_envs;
+    CUDA_OK(cudaMalloc(&h->d_am, 2 * sizeof(rs_agent_model)));
+    CUDA_OK(cudaMemcpy(h->d_am, agents, 2 * sizeof(rs_agent_model), cudaMemcpyHostToDevice));
+    EnvDev& d = h->d;
+    d.E = E; d.am = h->d_am; d.h = cfg->timestep; d.max_newton = cfg->newton_iters > 0 ? cfg->newton_iters : 8;
+    d.P.frame_skip = cfg->frame_skip; d.P.timestep_limit = cfg->timestep_limit; d.P.ring_limit = cfg->ring_limit;
+    d.P.init_pos_noise = cfg->init_pos_noise; d.P.init_vel_noise = cfg->init_vel_noise;
+    d.P.seed_lo = (uint32_t)cfg->seed; d.P.seed_hi = (uint32_t)(cfg->seed >> 32);
+    CUDA_OK(cudaMalloc(&d.qpos, sizeof(float) * E * h->nq)); CUDA_OK(cudaMalloc(&d.qvel, sizeof(float) * E * h->nv));
+    CUDA_OK(cudaMalloc(&d.warm, sizeof(float) * E * h->nv)); CUDA_OK(cudaMalloc(&d.ep_ret, sizeof(float) * E));
+    CUDA_OK(cudaMalloc(&d.ep_dret, sizeof(float) * E)); CUDA_OK(cudaMalloc(&d.ep_step, sizeof(int) * E));
+    CUDA_OK(cudaMalloc(&d.status, sizeof(int) * E)); CUDA_OK(cudaMalloc(&d.ep_count, sizeof(unsigned int) * E));
+    CUDA_OK(cudaMemset(d.qpos, 0, sizeof(float) * E * h->nq)); CUDA_OK(cudaMemset(d.qvel, 0, sizeof(float) * E * h->nv));
+    CUDA_OK(cudaMemset(d.warm, 0, sizeof(float) * E * h->nv)); CUDA_OK(cudaMemset(d.ep_ret, 0, sizeof(float) * E));
+    CUDA_OK(cudaMemset(d.ep_dret, 0, sizeof(float) * E)); CUDA_OK(cudaMemset(d.ep_step, 0, sizeof(int) * E));
+    CUDA_OK(cudaMemset(d.status, 0, sizeof(int) * E)); CUDA_OK(cudaMemset(d.ep_count, 0, sizeof(unsigned int) * E));
+    int rc = dispatch(h, [&](auto la, auto lb) {
+        constexpr int A = decltype(la)::value, B = decltype(lb)::value;
+        CUDA_OK(cudaFuncSetAttribute(k_step<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CUDA_OK(cudaFuncSetAttribute(k_reset<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CUDA_OK(cudaFuncSetAttribute(k_set_state<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CUDA_OK(cudaFuncSetAttribute(k_forward_debug<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        return RS_OK;
+    });
+    if (rc) { delete h; return rc; }
+    // host staging
+    const int OD = h->obsA + h->obsB;
+    CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaMallocHost(&h->h_act, sizeof(float) * E * h->nu)); CUDA_OK(cudaMallocHost(&h->h_obs, sizeof(float) * E * OD));
+    CUDA_OK(cudaMallocHost(&h->h_rew, sizeof(float) * E * 2)); CUDA_OK(cudaMallocHost(&h->h_info, sizeof(float) * E * 2 * RS_INFO_DIM));
+    CUDA_OK(cudaMallocHost(&h->h_epi, sizeof(float) * E * 3)); CUDA_OK(cudaMallocHost(&h->h_done, E * 2));
+    CUDA_OK(cudaMalloc(&h->s_act, sizeof(float) * E * h->nu)); CUDA_OK(cudaMalloc(&h->s_obs, sizeof(float) * E * OD));
+    CUDA_OK(cudaMalloc(&h->s_rew, sizeof(float) * E * 2)); CUDA_OK(cudaMalloc(&h->s_info, sizeof(float) * E * 2 * RS_INFO_DIM));
+    CUDA_OK(cudaMalloc(&h->s_epi, sizeof(float) * E * 3)); CUDA_OK(cudaMalloc(&h->s_done, E * 2));
+    *out = h;
+    return RS_OK;
+}
+
+void rs_destroy(rs_env* h) {
+    if (!h) return;
+    cudaFree(h->d_am); cudaFree(h->d.qpos); cudaFree(h->d.qvel); cudaFree(h->d.warm); cudaFree(h->d.ep_ret);
+    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.status); cudaFree(h->d.ep_count);
+    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_epi); cudaFreeHost(h->h_done);
+    cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_epi); cudaFree(h->s_done);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int rs_dims(const rs_env* h, int* nq, int* nv, int* nu, int* obs_a, int* obs_b, int* act_a, int* act_b) {
+    if (!h) return fail(RS_ERR_ARG, "rs_dims: null handle%s", "");
+    if (nq) *nq = h->nq; if (nv) *nv = h->nv; if (nu) *nu = h->nu;
+    if (obs_a) *obs_a = h->obsA; if (obs_b) *obs_b = h->obsB;
+    if (act_a) *act_a = 2 * h->LA; if (act_b) *act_b = 2 * h->LB;
+    return RS_OK;
+}
+
+#define GRID(h) dim3(((h)->d.E + RS_WPB - 1) / RS_WPB), dim3(32 * RS_WPB), (h)->smem, (cudaStream_t)stream
+
+int rs_reset(rs_env* h, const uint8_t* mask, float* obs, void* stream) {
+    if (!h) return fail(RS_ERR_ARG, "rs_reset: null handle%s", "");
+    return dispatch(h, [&](auto la, auto lb) {
+        k_reset<decltype(la)::value, decltype(lb)::value><<<GRID(h)>>>(h->d, mask, obs);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return RS_OK;
+    });
+}
+
+int rs_set_state(rs_env* h, const float* qpos, const float* qvel, float* obs, void* stream) {
+    if (!h || !qpos || !qvel) return fail(RS_ERR_ARG, "rs_set_state: bad argument%s", "");
+    return dispatch(h, [&](auto la, auto lb) {
+        k_set_state<decltype(la)::value, decltype(lb)::value><<<GRID(h)>>>(h->d, qpos, qvel, obs);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return RS_OK;
+    });
+}
+
+int rs_get_state(rs_env* h, float* qpos, float* qvel, int* ep_step, int* status, void* stream) {
+    if (!h) return fail(RS_ERR_ARG, "rs_get_state: null handle%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int E = h->d.E;
+    if (qpos) CUDA_OK(cudaMemcpyAsync(qpos, h->d.qpos, sizeof(float) * E * h->nq, cudaMemcpyDeviceToDevice, st));
+    if (qvel) CUDA_OK(cudaMemcpyAsync(qvel, h->d.qvel, sizeof(float) * E * h->nv, cudaMemcpyDeviceToDevice, st));
+    if (ep_step) CUDA_OK(cudaMemcpyAsync(ep_step, h->d.ep_step, sizeof(int) * E, cudaMemcpyDeviceToDevice, st));
+    if (status) CUDA_OK(cudaMemcpyAsync(status, h->d.status, sizeof(int) * E, cudaMemcpyDeviceToDevice, st));
+    return RS_OK;
+}
+
+int rs_step(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* done, float* info, float* episode,
+            int auto_reset, void* stream) {
+    if (!h || !actions || !obs || !rew || !done) return fail(RS_ERR_ARG, "rs_step: bad argument%s", "");
+    return dispatch(h, [&](auto la, auto lb) {
+        k_step<decltype(la)::value, decltype(lb)::value><<<GRID(h)>>>(h->d, actions, obs, rew, done, info, episode, auto_reset);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return RS_OK;
+    });
+}
+
+int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* done, float* info, float* episode,
+                 int auto_reset) {
+    if (!h || !actions || !obs || !rew || !done) return fail(RS_ERR_ARG, "rs_step_host: bad argument%s", "");
+    const int E = h->d.E, OD = h->obsA + h->obsB;
+    memcpy(h->h_act, actions, sizeof(float) * E * h->nu);
+    CUDA_OK(cudaMemcpyAsync(h->s_act, h->h_act, sizeof(float) * E * h->nu, cudaMemcpyHostToDevice, h->stream));
+    int rc = rs_step(h, h->s_act, h->s_obs, h->s_rew, h->s_done, h->s_info, h->s_epi, auto_reset, h->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(h->h_obs, h->s_obs, sizeof(float) * E * OD, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->h_rew, h->s_rew, sizeof(float) * E * 2, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->h_done, h->s_done, E * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (info) CUDA_OK(cudaMemcpyAsync(h->h_info, h->s_info, sizeof(float) * E * 2 * RS_INFO_DIM, cudaMemcpyDeviceToHost, h->stream));
+    if (episode) CUDA_OK(cudaMemcpyAsync(h->h_epi, h->s_epi, sizeof(float) * E * 3, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    memcpy(obs, h->h_obs, sizeof(float) * E * OD); memcpy(rew, h->h_rew, sizeof(float) * E * 2); memcpy(done, h->h_done, E * 2);
+    if (info) memcpy(info, h->h_info, sizeof(float) * E * 2 * RS_INFO_DIM);
+    if (episode) memcpy(episode, h->h_epi, sizeof(float) * E * 3);
+    return RS_OK;
+}
+
+int rs_forward_debug(rs_env* h, const float* ctrl, float* qacc, int* ncon, int* niter, void* stream) {
+    if (!h || !ctrl || !qacc || !ncon || !niter) return fail(RS_ERR_ARG, "rs_forward_debug: bad argument%s", "");
+    return dispatch(h, [&](auto la, auto lb) {
+        k_forward_debug<decltype(la)::value, decltype(lb)::value><<<GRID(h)>>>(h->d, ctrl, qacc, ncon, niter);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return RS_OK;
+    });
+}
+
+}  // extern "C"

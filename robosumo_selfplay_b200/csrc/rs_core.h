@@ -1,0 +1,950 @@
+// rs_core.h -- articulated-body + contact physics of one RoboSumo env pair, one warp per pair.
+//
+// Replaces what the reference gets from MuJoCo 2.1 through mujoco-py for this path
+// (robosumo/robosumo/envs/mujoco_env.py:104-129 -> mujoco-py/mujoco_py/mjsim.pyx:101-129;
+//  stage list mujoco-py/mujoco_py/pxd/mujoco.pxd:208-327; options assets/tatami.xml:3-6).
+//
+// Design (B200-first, not a MuJoCo port):
+//  * one warp owns one env pair; all per-pair state lives in a shared-memory slab for the
+//    whole env step (5 substeps x 4 RK stages = 20 forward evaluations), HBM is touched only
+//    at the start (state + action) and the end (state + obs + reward);
+//  * the body tree is exploited structurally: a floating torso group (torso + welded leg
+//    stubs, pre-merged at model-compile time) with L two-link legs -> closed-form spatial
+//    recursion per leg, no generic tree walk;
+//  * the constraint Jacobian is never stored: J*x is evaluated through body twists and
+//    J^T*f through body wrenches; H = M + J^T D J is assembled contact by contact from three
+//    direction Jacobians;
+//  * the soft-constraint problem is solved in the primal (Newton with exact line search on
+//    the one-sided quadratic rows of the pyramidal cone), which is the reference's configured
+//    solver, warm-started from the previous stage.
+//
+// Code is written as phases of independent "items" (RS_LANE_LOOP) separated by warp syncs
+// and communicating only through the slab, so that the same source also compiles as a
+// host emulation for the CPU unit tests (tests/emu).  The product builds the CUDA path only.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/rs_b200.h"
+
+#if defined(__CUDACC__)
+#define RS_HD __host__ __device__ __forceinline__
+#else
+#define RS_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define RS_LANE_LOOP(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+#define RS_SYNC() __syncwarp()
+#define RS_ATOMIC_ADDF(p, v) atomicAdd((p), (v))
+#define RS_ATOMIC_INC(p) atomicAdd((p), 1)
+#define RS_LANE0 ((threadIdx.x & 31) == 0)
+#else
+#define RS_LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
+#define RS_SYNC()
+#define RS_ATOMIC_ADDF(p, v) (*(p) += (v))
+#define RS_ATOMIC_INC(p) ((*(p))++)
+#define RS_LANE0 (true)
+#endif
+
+#define RS_MAXCON 32
+
+// scene constants (assets/tatami.xml, utils.py:64-88)
+#define RS_FLOOR_Z (-0.025f)
+#define RS_BOX_HX 2.3f
+#define RS_BOX_HZ 0.25f
+#define RS_BOX_CZ 0.25f
+#define RS_RAIL 2.0f
+#define RS_RAIL_Z 0.5f
+#define RS_RAIL_R 0.03f
+#define RS_MARGIN 0.01f
+#define RS_MU 1.0f
+#define RS_GRAV 9.81f
+// solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2)  [MuJoCo defaults]
+#define RS_DMIN 0.9f
+#define RS_DMAX 0.95f
+#define RS_WIDTH 0.001f
+
+namespace rs {
+
+struct V3 { float x, y, z; };
+RS_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RS_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+RS_HD void st3(float* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+RS_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RS_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RS_HD V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+RS_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RS_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RS_HD float norm(V3 a) { return sqrtf(dot(a, a)); }
+RS_HD V3 normalized(V3 a, float* len) {
+    float n = norm(a);
+    *len = n;
+    if (n < 1e-12f) return v3(1.f, 0.f, 0.f);
+    float s = 1.f / n;
+    return s * a;
+}
+// R (row-major 3x3) * v  and  R^T * v
+RS_HD V3 mulR(const float* R, V3 v) { return v3(R[0]*v.x + R[1]*v.y + R[2]*v.z, R[3]*v.x + R[4]*v.y + R[5]*v.z, R[6]*v.x + R[7]*v.y + R[8]*v.z); }
+RS_HD V3 mulRT(const float* R, V3 v) { return v3(R[0]*v.x + R[3]*v.y + R[6]*v.z, R[1]*v.x + R[4]*v.y + R[7]*v.z, R[2]*v.x + R[5]*v.y + R[8]*v.z); }
+// Rodrigues rotation of v about unit axis a by angle (s = sin, c = cos)
+RS_HD V3 rot(V3 a, float s, float c, V3 v) { return c * v + s * cross(a, v) + ((1.f - c) * dot(a, v)) * a; }
+
+template <int LA, int LB>
+struct Slab {
+    enum {
+        LT = LA + LB, NQA = 7 + 2 * LA, NVA = 6 + 2 * LA, NQ = 14 + 2 * LT, NV = 12 + 2 * LT, NU = 2 * LT,
+        NVP = (NV | 1), NB = 2 + 2 * LT, NG = 2 + 3 * LT, NGA = 1 + 3 * LA, NGB = 1 + 3 * LB
+    };
+    float q[NQ], v[NV], q0[NQ], v0[NV], vsum[NV], asum[NV];
+    float x[NV];      // qacc: Newton iterate, warm start across stages / steps
+    float tau[NV];    // qfrc_smooth = passive + actuator - bias
+    float r[NV];      // M x - tau
+    float d[NV];      // Newton direction
+    float Md[NV];
+    float jtf[NV];
+    float act[NU];    // gear * clip(ctrl)
+    float Rt[2][9];   // torso rotation matrices
+    float org[NB][3]; // body origins: [a] torso a, [2+g] hip of leg g, [2+LT+g] ankle of leg g
+    float tip[LT][3];
+    float axh[LT][3], axa[LT][3];   // joint axes in world
+    float legI[LT][10];             // leg subtree spatial inertia about its torso origin: m, m*c, I(xx,xy,xz,yy,yz,zz)
+    float legF[LT][6];              // leg subtree (torque about torso origin / hip origin, force)
+    float tw[NB][6];                // body twists (omega, v at body origin)
+    float wr[NB][6];                // body wrenches (torque about body origin, force)
+    float M[NV * NVP];
+    float H[NV * NVP];
+    // contacts
+    float cpos[RS_MAXCON][3], cfr[RS_MAXCON][9], cdist[RS_MAXCON], ctran[RS_MAXCON], cD[RS_MAXCON];
+    float caref[RS_MAXCON][4], cjar[RS_MAXCON][4], cjd[RS_MAXCON][4];
+    int cbA[RS_MAXCON], cbB[RS_MAXCON];
+    // joint limits (one potential row per hinge)
+    float lsgn[NU], lD[NU], laref[NU], ljar[NU], ljd[NU];
+    float red[64];
+    float scr[2][64];               // per-contact direction Jacobians: idx(16 as float) + 3 x 16
+    int ncon, status, niter, same;
+};
+
+template <int LA, int LB>
+struct Ctx {
+    typedef Slab<LA, LB> S;
+    S* s;
+    const rs_agent_model* am;   // [2]
+    float h;                    // timestep
+    int max_newton;
+    RS_HD int L(int a) const { return a ? LB : LA; }
+    RS_HD int qadr(int a) const { return a ? S::NQA : 0; }
+    RS_HD int vadr(int a) const { return a ? S::NVA : 0; }
+    RS_HD int leg0(int a) const { return a ? LA : 0; }
+    RS_HD int agent_of_leg(int g) const { return g >= LA ? 1 : 0; }
+    RS_HD int hipdof(int g) const { int a = agent_of_leg(g); return vadr(a) + 6 + 2 * (g - leg0(a)); }
+    RS_HD int hipq(int g) const { int a = agent_of_leg(g); return qadr(a) + 7 + 2 * (g - leg0(a)); }
+    RS_HD int bhip(int g) const { return 2 + g; }
+    RS_HD int bank(int g) const { return 2 + S::LT + g; }
+};
+
+// ------------------------------------------------------------------------------------------
+// kinematics (mj_kinematics): normalises the free-joint quaternions in q in place
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+RS_HD void fk(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(a, 2) {
+        float* qq = s.q + c.qadr(a);
+        float w = qq[3], x = qq[4], y = qq[5], z = qq[6];
+        float n = sqrtf(w * w + x * x + y * y + z * z);
+        if (n < 1e-12f) { w = 1.f; x = y = z = 0.f; } else { float inv = 1.f / n; w *= inv; x *= inv; y *= inv; z *= inv; }
+        qq[3] = w; qq[4] = x; qq[5] = y; qq[6] = z;
+        float* R = s.Rt[a];
+        R[0] = w*w + x*x - y*y - z*z; R[1] = 2.f*(x*y - w*z);         R[2] = 2.f*(x*z + w*y);
+        R[3] = 2.f*(x*y + w*z);       R[4] = w*w - x*x + y*y - z*z;   R[5] = 2.f*(y*z - w*x);
+        R[6] = 2.f*(x*z - w*y);       R[7] = 2.f*(y*z + w*x);         R[8] = w*w - x*x - y*y + z*z;
+        s.org[a][0] = qq[0]; s.org[a][1] = qq[1]; s.org[a][2] = qq[2];
+    }
+    RS_SYNC();
+    RS_LANE_LOOP(g, S::LT) {
+        int a = c.agent_of_leg(g), l = g - c.leg0(a);
+        const rs_agent_model& m = c.am[a];
+        const float* R = s.Rt[a];
+        V3 pt = ld3(s.org[a]);
+        float qh = s.q[c.hipq(g)], qa = s.q[c.hipq(g) + 1];
+        float sh, ch, sa, ca;
+        sincosf(qh, &sh, &ch); sincosf(qa, &sa, &ca);
+        V3 axh = ld3(m.ax_hip[l]), axa = ld3(m.ax_ank[l]);
+        V3 ph = pt + mulR(R, ld3(m.r_hip[l]));
+        V3 pa = ph + mulR(R, rot(axh, sh, ch, ld3(m.r_ank[l])));
+        V3 tipl = rot(axh, sh, ch, rot(axa, sa, ca, ld3(m.e_ank[l])));
+        st3(s.org[c.bhip(g)], ph);
+        st3(s.org[c.bank(g)], pa);
+        st3(s.tip[g], pa + mulR(R, tipl));
+        st3(s.axh[g], mulR(R, axh));
+        st3(s.axa[g], mulR(R, rot(axh, sh, ch, axa)));
+    }
+    RS_SYNC();
+}
+
+// spatial inertia of a capsule body about origin O (world axes), applied to a motion (w, vO):
+// returns momentum-like pair (n about O, f)
+struct Cap { float m, ip, ia; V3 c, u; };   // mass, perpendicular / axial inertia, com (rel. O), axis
+RS_HD void applyI(const Cap& b, V3 w, V3 vO, V3* n, V3* f) {
+    V3 vc = vO + cross(w, b.c);
+    *f = b.m * vc;
+    V3 Iw = b.ip * w + ((b.ia - b.ip) * dot(b.u, w)) * b.u;
+    *n = Iw + cross(b.c, *f);
+}
+// accumulate the 10 spatial-inertia numbers of a capsule about O
+RS_HD void accI(const Cap& b, float* I10) {
+    I10[0] += b.m;
+    I10[1] += b.m * b.c.x; I10[2] += b.m * b.c.y; I10[3] += b.m * b.c.z;
+    float cc = dot(b.c, b.c), k = b.ia - b.ip;
+    I10[4] += b.ip + k * b.u.x * b.u.x + b.m * (cc - b.c.x * b.c.x);
+    I10[5] += k * b.u.x * b.u.y - b.m * b.c.x * b.c.y;
+    I10[6] += k * b.u.x * b.u.z - b.m * b.c.x * b.c.z;
+    I10[7] += b.ip + k * b.u.y * b.u.y + b.m * (cc - b.c.y * b.c.y);
+    I10[8] += k * b.u.y * b.u.z - b.m * b.c.y * b.c.z;
+    I10[9] += b.ip + k * b.u.z * b.u.z + b.m * (cc - b.c.z * b.c.z);
+}
+// body force of RNE: f = I a + v x* (I v)
+RS_HD void bodyForce(const Cap& b, V3 w, V3 vO, V3 al, V3 aO, V3* n, V3* f) {
+    V3 hn, hf, an, af;
+    applyI(b, w, vO, &hn, &hf);
+    applyI(b, al, aO, &an, &af);
+    *n = an + cross(w, hn) + cross(vO, hf);
+    *f = af + cross(w, hf);
+}
+
+// ------------------------------------------------------------------------------------------
+// joint-space inertia M (mj_crb) and smooth forces tau = passive + actuator - bias (mj_rne,
+// mj_passive, mj_fwdActuation).  Reference point for agent a: its torso origin (an inertial
+// point coincident with it at this instant), world-aligned axes.
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+RS_HD void dynamics(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    const int NVP = S::NVP;
+    RS_LANE_LOOP(g, S::LT) {
+        int a = c.agent_of_leg(g), l = g - c.leg0(a);
+        const rs_agent_model& m = c.am[a];
+        const float* R = s.Rt[a];
+        int va = c.vadr(a), dh = c.hipdof(g), da = dh + 1;
+        V3 O = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]) - O, pa = ld3(s.org[c.bank(g)]) - O, pt = ld3(s.tip[g]) - O;
+        V3 axh = ld3(s.axh[g]), axa = ld3(s.axa[g]);
+        float len;
+        Cap hip, ank;
+        hip.m = m.m_hip[l]; hip.ip = m.ip_hip[l]; hip.ia = m.ia_hip[l]; hip.c = 0.5f * (ph + pa); hip.u = normalized(pa - ph, &len);
+        ank.m = m.m_ank[l]; ank.ip = m.ip_ank[l]; ank.ia = m.ia_ank[l]; ank.c = 0.5f * (pa + pt); ank.u = normalized(pt - pa, &len);
+        // motion subspaces about O: rotation about axis through point p  ->  (axis, axis x (O - p)) = (axis, -axis x p)
+        V3 sa_v = cross(pa, axa), sh_v = cross(ph, axh);
+        V3 nA, fA, nH, fH, n2, f2;
+        applyI(ank, axa, sa_v, &nA, &fA);                       // I_ank s_a
+        applyI(hip, axh, sh_v, &nH, &fH);                       // (I_hip + I_ank) s_h
+        applyI(ank, axh, sh_v, &n2, &f2);
+        nH = nH + n2; fH = fH + f2;
+        float Maa = dot(axa, nA) + dot(sa_v, fA) + m.armature;
+        float Mha = dot(axh, nA) + dot(sh_v, fA);
+        float Mhh = dot(axh, nH) + dot(sh_v, fH) + m.armature;
+        s.M[da * NVP + da] = Maa; s.M[dh * NVP + da] = Mha; s.M[da * NVP + dh] = Mha; s.M[dh * NVP + dh] = Mhh;
+        V3 rA = mulRT(R, nA), rH = mulRT(R, nH);
+        float colA[6] = { fA.x, fA.y, fA.z, rA.x, rA.y, rA.z }, colH[6] = { fH.x, fH.y, fH.z, rH.x, rH.y, rH.z };
+        for (int k = 0; k < 6; k++) {
+            s.M[(va + k) * NVP + da] = colA[k]; s.M[da * NVP + va + k] = colA[k];
+            s.M[(va + k) * NVP + dh] = colH[k]; s.M[dh * NVP + va + k] = colH[k];
+        }
+        float I10[10];
+        for (int k = 0; k < 10; k++) I10[k] = 0.f;
+        accI(hip, I10); accI(ank, I10);
+        for (int k = 0; k < 10; k++) s.legI[g][k] = I10[k];
+        // ---- RNE with qacc = 0 ----
+        const float* vv = s.v + va;
+        V3 wt = mulR(R, v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
+        V3 at_lin = cross(vt, wt);  at_lin.z += RS_GRAV;        // spatial accel of torso: (0, -w x v - g)
+        float qdh = s.v[dh], qda = s.v[da];
+        // hip body: v = v_t + s_h qd ; a = a_t + (v_t x s_h) qd
+        V3 wh = wt + qdh * axh, vh = vt + qdh * sh_v;
+        V3 alh = qdh * cross(wt, axh);
+        V3 ah = at_lin + qdh * (cross(wt, sh_v) + cross(vt, axh));
+        // ankle body: a = a_h + (v_h x s_a) qd
+        V3 wa = wh + qda * axa, vaO = vh + qda * sa_v;
+        V3 ala = alh + qda * cross(wh, axa);
+        V3 aa = ah + qda * (cross(wh, sa_v) + cross(vh, axa));
+        V3 nFa, fFa, nFh, fFh;
+        bodyForce(ank, wa, vaO, ala, aa, &nFa, &fFa);
+        bodyForce(hip, wh, vh, alh, ah, &nFh, &fFh);
+        nFh = nFh + nFa; fFh = fFh + fFa;                       // hip subtree
+        float bias_a = dot(axa, nFa) + dot(sa_v, fFa);
+        float bias_h = dot(axh, nFh) + dot(sh_v, fFh);
+        int ua = (a ? 2 * LA : 0) + 2 * l;
+        s.tau[dh] = -m.damping * qdh + s.act[ua] - bias_h;
+        s.tau[da] = -m.damping * qda + s.act[ua + 1] - bias_a;
+        s.legF[g][0] = nFh.x; s.legF[g][1] = nFh.y; s.legF[g][2] = nFh.z;
+        s.legF[g][3] = fFh.x; s.legF[g][4] = fFh.y; s.legF[g][5] = fFh.z;
+    }
+    RS_SYNC();
+    RS_LANE_LOOP(a, 2) {
+        const rs_agent_model& m = c.am[a];
+        const float* R = s.Rt[a];
+        int va = c.vadr(a);
+        // torso group in world axes about the torso origin
+        V3 cT = mulR(R, ld3(m.cT));
+        float IT[9];   // R IT R^T
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+            float acc = 0.f;
+            for (int p = 0; p < 3; p++) for (int q = 0; q < 3; q++) acc += R[3*i + p] * m.IT[3*p + q] * R[3*j + q];
+            IT[3*i + j] = acc;
+        }
+        float I10[10];
+        float cc = dot(cT, cT);
+        I10[0] = m.mT; I10[1] = m.mT * cT.x; I10[2] = m.mT * cT.y; I10[3] = m.mT * cT.z;
+        I10[4] = IT[0] + m.mT * (cc - cT.x * cT.x); I10[5] = IT[1] - m.mT * cT.x * cT.y; I10[6] = IT[2] - m.mT * cT.x * cT.z;
+        I10[7] = IT[4] + m.mT * (cc - cT.y * cT.y); I10[8] = IT[5] - m.mT * cT.y * cT.z; I10[9] = IT[8] + m.mT * (cc - cT.z * cT.z);
+        V3 nsum = v3(0, 0, 0), fsum = v3(0, 0, 0);
+        for (int l = 0; l < c.L(a); l++) {
+            int g = c.leg0(a) + l;
+            for (int k = 0; k < 10; k++) I10[k] += s.legI[g][k];
+            nsum = nsum + ld3(s.legF[g]); fsum = fsum + ld3(s.legF[g] + 3);
+        }
+        float mt = I10[0];
+        V3 mc = v3(I10[1], I10[2], I10[3]);
+        // root block: lin-lin m I ; lin-ang: column k = (R e_k) x mc ; ang-ang: R^T I_O R
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) s.M[(va + i) * S::NVP + va + j] = (i == j) ? mt : 0.f;
+        float IO[9] = { I10[4], I10[5], I10[6], I10[5], I10[7], I10[8], I10[6], I10[8], I10[9] };
+        for (int k = 0; k < 3; k++) {
+            V3 ek = v3(R[k], R[3 + k], R[6 + k]);
+            V3 f = cross(ek, mc);
+            V3 n = mulR(IO, ek);
+            V3 nb = mulRT(R, n);
+            s.M[(va + 0) * S::NVP + va + 3 + k] = f.x; s.M[(va + 3 + k) * S::NVP + va + 0] = f.x;
+            s.M[(va + 1) * S::NVP + va + 3 + k] = f.y; s.M[(va + 3 + k) * S::NVP + va + 1] = f.y;
+            s.M[(va + 2) * S::NVP + va + 3 + k] = f.z; s.M[(va + 3 + k) * S::NVP + va + 2] = f.z;
+            s.M[(va + 3) * S::NVP + va + 3 + k] = nb.x; s.M[(va + 4) * S::NVP + va + 3 + k] = nb.y; s.M[(va + 5) * S::NVP + va + 3 + k] = nb.z;
+        }
+        // torso group RNE
+        const float* vv = s.v + va;
+        V3 wt = mulR(R, v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
+        V3 at_lin = cross(vt, wt);  at_lin.z += RS_GRAV;
+        // generic (full inertia) body force for the torso group
+        V3 vc = vt + cross(wt, cT);
+        V3 hf = m.mT * vc;
+        V3 hn = mulR(IT, wt) + cross(cT, hf);
+        V3 af = m.mT * at_lin;               // alpha = 0
+        V3 an = cross(cT, af);
+        V3 nT = an + cross(wt, hn) + cross(vt, hf);
+        V3 fT = af + cross(wt, hf);
+        nT = nT + nsum; fT = fT + fsum;
+        V3 nb = mulRT(R, nT);
+        s.tau[va + 0] = -fT.x; s.tau[va + 1] = -fT.y; s.tau[va + 2] = -fT.z;
+        s.tau[va + 3] = -nb.x; s.tau[va + 4] = -nb.y; s.tau[va + 5] = -nb.z;
+    }
+    RS_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------
+// collision (mj_collision restricted to the pairs this scene can produce)
+// ------------------------------------------------------------------------------------------
+RS_HD void make_frame(V3 n, V3 yhint, float* fr) {   // mju_makeFrame
+    V3 y = yhint;
+    if (dot(y, y) < 0.25f) { y = (n.y < 0.5f && n.y > -0.5f) ? v3(0.f, 1.f, 0.f) : v3(0.f, 0.f, 1.f); }
+    float len;
+    y = normalized(y - dot(n, y) * n, &len);
+    V3 z = cross(n, y);
+    st3(fr, n); st3(fr + 3, y); st3(fr + 6, z);
+}
+
+template <int LA, int LB>
+RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n, V3 yhint, float tran) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    if (!(dist < RS_MARGIN)) return;
+    int k = RS_ATOMIC_INC(&s.ncon);
+    if (k >= RS_MAXCON) return;    // counted, dropped: status flag raised by the caller
+    s.cbA[k] = bA; s.cbB[k] = bB; s.cdist[k] = dist; s.ctran[k] = tran;
+    st3(s.cpos[k], pos);
+    make_frame(n, yhint, s.cfr[k]);
+}
+
+// sphere (centre cA, radius rA, side A) against sphere (cB, rB, side B): normal A -> B
+template <int LA, int LB>
+RS_HD void sph_sph(Ctx<LA, LB>& c, int bA, int bB, V3 cA, float rA, V3 cB, float rB, float tran) {
+    float len;
+    V3 n = normalized(cB - cA, &len);
+    float dist = len - rA - rB;
+    if (dist < RS_MARGIN) add_contact(c, bA, bB, dist, cA + (rA + 0.5f * dist) * n, n, v3(0, 0, 0), tran);
+}
+RS_HD V3 seg_nearest(V3 e0, V3 e1, V3 p) {
+    V3 d = e1 - e0;
+    float dd = dot(d, d);
+    float t = dd > 1e-20f ? dot(p - e0, d) / dd : 0.f;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    return e0 + t * d;
+}
+// closest points of two segments given as centre/axis/half-length (mjc_CapsuleCapsule parametrisation)
+RS_HD void seg_seg(V3 p1, V3 a1, float l1, V3 p2, V3 a2, float l2, V3* o1, V3* o2) {
+    V3 dif = p1 - p2;
+    float mb = -dot(a1, a2), u = -dot(a1, dif), v = dot(a2, dif);
+    float det = 1.f - mb * mb;
+    float x1, x2;
+    if (fabsf(det) >= 1e-6f) {
+        x1 = (u - mb * v) / det; x2 = (v - mb * u) / det;
+        if (x1 > l1) { x1 = l1; x2 = v - mb * l1; } else if (x1 < -l1) { x1 = -l1; x2 = v + mb * l1; }
+        if (x2 > l2) { x2 = l2; x1 = u - mb * l2; } else if (x2 < -l2) { x2 = -l2; x1 = u + mb * l2; }
+        if (x1 > l1) x1 = l1; else if (x1 < -l1) x1 = -l1;
+    } else {   // (near-)parallel: centre of the overlap interval
+        x1 = fminf(fmaxf(u, -l1), l1);
+        x2 = fminf(fmaxf(v - mb * x1, -l2), l2);
+    }
+    *o1 = p1 + x1 * a1; *o2 = p2 + x2 * a2;
+}
+
+// geom i of the pair: 0/1 torso spheres, then per global leg g: aux, hip, ankle capsules
+template <int LA, int LB>
+RS_HD void geom_of(const Ctx<LA, LB>& c, int i, V3* e0, V3* e1, float* r, int* body, float* iw, int* agent, bool* sphere) {
+    typedef Slab<LA, LB> S;
+    const S& s = *c.s;
+    if (i < 2) {
+        *e0 = *e1 = ld3(s.org[i]); *r = c.am[i].torso_r; *body = i; *iw = c.am[i].iw_torso; *agent = i; *sphere = true;
+        return;
+    }
+    int k = i - 2, g = k / 3, kind = k - 3 * g;
+    int a = c.agent_of_leg(g), l = g - c.leg0(a);
+    *agent = a; *sphere = false; *r = c.am[a].leg_r;
+    if (kind == 0) { *e0 = ld3(s.org[a]); *e1 = ld3(s.org[c.bhip(g)]); *body = a; *iw = c.am[a].iw_aux[l]; }
+    else if (kind == 1) { *e0 = ld3(s.org[c.bhip(g)]); *e1 = ld3(s.org[c.bank(g)]); *body = c.bhip(g); *iw = c.am[a].iw_hip[l]; }
+    else { *e0 = ld3(s.org[c.bank(g)]); *e1 = ld3(s.tip[g]); *body = c.bank(g); *iw = c.am[a].iw_ank[l]; }
+}
+
+template <int LA, int LB>
+RS_HD void sphere_vs_world(Ctx<LA, LB>& c, int body, V3 p, float r, float iw, V3 yhint, bool rails, bool floor_too) {
+    // floor plane z = RS_FLOOR_Z, normal +z
+    if (floor_too) {
+        float dist = p.z - RS_FLOOR_Z - r;
+        if (dist < RS_MARGIN) add_contact(c, -1, body, dist, v3(p.x, p.y, p.z - r - 0.5f * dist), v3(0.f, 0.f, 1.f), yhint, iw);
+    }
+    // tatami box: centre (0,0,RS_BOX_CZ), half (RS_BOX_HX, RS_BOX_HX, RS_BOX_HZ)
+    {
+        V3 loc = v3(p.x, p.y, p.z - RS_BOX_CZ);
+        V3 cl = v3(fminf(fmaxf(loc.x, -RS_BOX_HX), RS_BOX_HX), fminf(fmaxf(loc.y, -RS_BOX_HX), RS_BOX_HX), fminf(fmaxf(loc.z, -RS_BOX_HZ), RS_BOX_HZ));
+        bool outside = (cl.x != loc.x) || (cl.y != loc.y) || (cl.z != loc.z);
+        if (outside) {
+            float len;
+            V3 n = normalized(loc - cl, &len);     // from box to sphere
+            float dist = len - r;
+            if (dist < RS_MARGIN) add_contact(c, -1, body, dist, v3(cl.x, cl.y, cl.z + RS_BOX_CZ) + (0.5f * dist) * n, n, v3(0, 0, 0), iw);
+        } else {
+            float px = RS_BOX_HX - fabsf(loc.x), py = RS_BOX_HX - fabsf(loc.y), pz = RS_BOX_HZ - fabsf(loc.z);
+            V3 n; float best;
+            if (px <= py && px <= pz) { best = px; n = v3(loc.x >= 0.f ? 1.f : -1.f, 0.f, 0.f); }
+            else if (py <= pz) { best = py; n = v3(0.f, loc.y >= 0.f ? 1.f : -1.f, 0.f); }
+            else { best = pz; n = v3(0.f, 0.f, loc.z >= 0.f ? 1.f : -1.f); }
+            float dist = -best - r;
+            add_contact(c, -1, body, dist, v3(loc.x, loc.y, loc.z + RS_BOX_CZ) + (-r - 0.5f * dist) * n, n, v3(0, 0, 0), iw);
+        }
+    }
+    (void)rails;
+}
+
+template <int LA, int LB>
+RS_HD void collide(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    if (RS_LANE0) s.ncon = 0;
+    RS_SYNC();
+    // --- agent geoms against the world (floor plane, tatami box, four border rails) ---
+    RS_LANE_LOOP(i, S::NG) {
+        V3 e0, e1; float r, iw; int body, agent; bool sph;
+        geom_of(c, i, &e0, &e1, &r, &body, &iw, &agent, &sph);
+        float len = 0.f;
+        V3 ax = sph ? v3(0, 0, 0) : normalized(e1 - e0, &len);
+        // MuJoCo's capsule geom frame has z = from - to; the plane-capsule routine emits the +z end first
+        sphere_vs_world(c, body, sph ? e0 : e0, r, iw, ax, true, true);
+        if (!sph) sphere_vs_world(c, body, e1, r, iw, ax, true, true);
+        // rails (thin cylinders treated as capsules of radius RS_RAIL_R)
+        float mx = fmaxf(fabsf(e0.x), fabsf(e1.x)) + r + RS_MARGIN + RS_RAIL_R;
+        float my = fmaxf(fabsf(e0.y), fabsf(e1.y)) + r + RS_MARGIN + RS_RAIL_R;
+        float zlo = fminf(e0.z, e1.z) - r - RS_MARGIN - RS_RAIL_R;
+        if ((mx >= RS_RAIL || my >= RS_RAIL) && zlo < RS_RAIL_Z) {
+            for (int k = 0; k < 4; k++) {
+                // top: y=+2 along x; right: x=+2 along y; bottom: y=-2 along x; left: x=-2 along y
+                V3 rp = (k == 0) ? v3(0.f, RS_RAIL, RS_RAIL_Z) : (k == 1) ? v3(RS_RAIL, 0.f, RS_RAIL_Z) : (k == 2) ? v3(0.f, -RS_RAIL, RS_RAIL_Z) : v3(-RS_RAIL, 0.f, RS_RAIL_Z);
+                V3 ra = (k & 1) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
+                V3 pg, pr;
+                if (sph) { pg = e0; pr = seg_nearest(rp - RS_RAIL * ra, rp + RS_RAIL * ra, e0); }
+                else seg_seg(0.5f * (e0 + e1), ax, 0.5f * len, rp, ra, RS_RAIL, &pg, &pr);
+                sph_sph(c, -1, body, pr, RS_RAIL_R, pg, r, iw);
+            }
+        }
+    }
+    // --- agent 0 geoms against agent 1 geoms ---
+    {
+        V3 dt = ld3(s.org[1]) - ld3(s.org[0]);
+        float reach = c.am[0].reach + c.am[1].reach + RS_MARGIN;
+        if (dot(dt, dt) < reach * reach) {
+            RS_LANE_LOOP(p, S::NGA * S::NGB) {
+                int ia = p / S::NGB, ib = p - ia * S::NGB;
+                // pair geom indices: agent 0 torso = 0, its leg geoms 2..2+3LA ; agent 1 torso = 1, leg geoms after
+                int gi = ia == 0 ? 0 : 1 + ia, gj = ib == 0 ? 1 : 1 + 3 * LA + ib;
+                V3 a0, a1, b0, b1; float rA, rB, iwA, iwB; int bA, bB, agA, agB; bool sA, sB;
+                geom_of(c, gi, &a0, &a1, &rA, &bA, &iwA, &agA, &sA);
+                geom_of(c, gj, &b0, &b1, &rB, &bB, &iwB, &agB, &sB);
+                V3 ca = 0.5f * (a0 + a1), cb = 0.5f * (b0 + b1);
+                float la, lb;
+                V3 ua = normalized(a1 - a0, &la), ub = normalized(b1 - b0, &lb);
+                float bound = 0.5f * (la + lb) + rA + rB + RS_MARGIN;
+                V3 dc = cb - ca;
+                if (dot(dc, dc) < bound * bound) {
+                    V3 pA, pB;
+                    if (sA && sB) { pA = a0; pB = b0; }
+                    else if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
+                    else if (sB) { pB = b0; pA = seg_nearest(a0, a1, b0); }
+                    else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
+                    sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB);
+                }
+            }
+        }
+    }
+    RS_SYNC();
+    if (s.ncon > RS_MAXCON) { if (RS_LANE0) { s.ncon = RS_MAXCON; s.status |= RS_STATUS_CONTACT_FULL; } }
+    RS_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------
+// twists: body velocities generated by a generalized vector `vec` (J x without storing J)
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+RS_HD void twists(Ctx<LA, LB>& c, const float* vec) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(g, S::LT) {
+        int a = c.agent_of_leg(g);
+        const float* vv = vec + c.vadr(a);
+        V3 wt = mulR(s.Rt[a], v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
+        if (g == c.leg0(a)) { st3(s.tw[a], wt); st3(s.tw[a] + 3, vt); }
+        V3 pt = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]), pa = ld3(s.org[c.bank(g)]);
+        int dh = c.hipdof(g);
+        V3 vh = vt + cross(wt, ph - pt);
+        V3 wh = wt + vec[dh] * ld3(s.axh[g]);
+        V3 vk = vh + cross(wh, pa - ph);
+        V3 wk = wh + vec[dh + 1] * ld3(s.axa[g]);
+        st3(s.tw[c.bhip(g)], wh); st3(s.tw[c.bhip(g)] + 3, vh);
+        st3(s.tw[c.bank(g)], wk); st3(s.tw[c.bank(g)] + 3, vk);
+    }
+    RS_SYNC();
+}
+template <int LA, int LB>
+RS_HD V3 point_vel(const Slab<LA, LB>& s, int b, V3 p) {
+    if (b < 0) return v3(0, 0, 0);
+    return ld3(s.tw[b] + 3) + cross(ld3(s.tw[b]), p - ld3(s.org[b]));
+}
+// rows of J * vec for every contact (4 pyramid rows) and every limit row, after twists(vec)
+template <int LA, int LB>
+RS_HD void rows_of(Ctx<LA, LB>& c, const float* vec, float (*cout)[4], float* lout) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(k, s.ncon) {
+        V3 p = ld3(s.cpos[k]);
+        V3 rel = point_vel(s, s.cbB[k], p) - point_vel(s, s.cbA[k], p);
+        float un = dot(ld3(s.cfr[k]), rel), u1 = dot(ld3(s.cfr[k] + 3), rel), u2 = dot(ld3(s.cfr[k] + 6), rel);
+        cout[k][0] = un + RS_MU * u1; cout[k][1] = un - RS_MU * u1; cout[k][2] = un + RS_MU * u2; cout[k][3] = un - RS_MU * u2;
+    }
+    RS_LANE_LOOP(j, S::NU) {
+        int g = j >> 1;
+        lout[j] = s.lsgn[j] * vec[c.hipdof(g) + (j & 1)];
+    }
+    RS_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------
+// constraint parameters (mj_makeConstraint + mj_makeImpedance): limits, pyramidal contacts
+// ------------------------------------------------------------------------------------------
+RS_HD float impedance(float pos_minus_margin) {
+    float x = fabsf(pos_minus_margin) / RS_WIDTH;
+    float y;
+    if (x >= 1.f) y = 1.f; else if (x <= 0.5f) y = 2.f * x * x; else y = 1.f - 2.f * (1.f - x) * (1.f - x);
+    return RS_DMIN + y * (RS_DMAX - RS_DMIN);
+}
+template <int LA, int LB>
+RS_HD void make_constraints(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    const float tc = fmaxf(0.02f, 2.f * c.h);
+    const float Kc = 1.f / (RS_DMAX * RS_DMAX * tc * tc), Bc = 2.f / (RS_DMAX * tc);
+    // limits first: sign and D, then J v through rows_of
+    RS_LANE_LOOP(j, S::NU) {
+        int g = j >> 1, a = c.agent_of_leg(g), l = g - c.leg0(a), isank = j & 1;
+        const rs_agent_model& m = c.am[a];
+        float qv = s.q[c.hipq(g) + isank];
+        float lo = isank ? m.lo_ank[l] : m.lo_hip[l], hi = isank ? m.hi_ank[l] : m.hi_hip[l];
+        float sgn = 0.f, pos = 0.f;
+        if (qv - lo < 0.f) { sgn = 1.f; pos = qv - lo; } else if (hi - qv < 0.f) { sgn = -1.f; pos = hi - qv; }
+        s.lsgn[j] = sgn;
+        float imp = impedance(pos);
+        float diag = isank ? m.iwd_ank[l] : m.iwd_hip[l];
+        float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
+        s.lD[j] = sgn != 0.f ? 1.f / R : 0.f;
+        s.laref[j] = -Kc * imp * pos;           // velocity term added below
+    }
+    RS_SYNC();
+    twists(c, s.v);
+    rows_of(c, s.v, s.cjd, s.ljd);              // J v (scratch in cjd / ljd)
+    RS_LANE_LOOP(j, S::NU) { s.laref[j] -= Bc * s.ljd[j]; }
+    RS_LANE_LOOP(k, s.ncon) {
+        float pm = s.cdist[k] - RS_MARGIN;
+        float imp = impedance(pm);
+        float diag = s.ctran[k] * (1.f + RS_MU * RS_MU);
+        float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
+        R = 2.f * RS_MU * RS_MU * R;
+        s.cD[k] = 1.f / R;
+        for (int r = 0; r < 4; r++) s.caref[k][r] = -Bc * s.cjd[k][r] - Kc * imp * pm;
+    }
+    RS_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------
+// J^T f through body wrenches
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+RS_HD void jt_forces(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NB * 6) { (&s.wr[0][0])[i] = 0.f; }
+    RS_SYNC();
+    RS_LANE_LOOP(k, s.ncon) {
+        float D = s.cD[k], f[4];
+        for (int r = 0; r < 4; r++) { float j = s.cjar[k][r]; f[r] = j < 0.f ? -D * j : 0.f; }
+        float fn = f[0] + f[1] + f[2] + f[3];
+        if (fn > 0.f) {
+            V3 F = fn * ld3(s.cfr[k]) + (RS_MU * (f[0] - f[1])) * ld3(s.cfr[k] + 3) + (RS_MU * (f[2] - f[3])) * ld3(s.cfr[k] + 6);
+            V3 p = ld3(s.cpos[k]);
+            for (int side = 0; side < 2; side++) {
+                int b = side ? s.cbB[k] : s.cbA[k];
+                if (b < 0) continue;
+                V3 Fs = side ? F : (-1.f) * F;
+                V3 T = cross(p - ld3(s.org[b]), Fs);
+                RS_ATOMIC_ADDF(&s.wr[b][0], T.x); RS_ATOMIC_ADDF(&s.wr[b][1], T.y); RS_ATOMIC_ADDF(&s.wr[b][2], T.z);
+                RS_ATOMIC_ADDF(&s.wr[b][3], Fs.x); RS_ATOMIC_ADDF(&s.wr[b][4], Fs.y); RS_ATOMIC_ADDF(&s.wr[b][5], Fs.z);
+            }
+        }
+    }
+    RS_SYNC();
+    RS_LANE_LOOP(g, S::LT) {
+        int dh = c.hipdof(g);
+        V3 ph = ld3(s.org[c.bhip(g)]), pa = ld3(s.org[c.bank(g)]);
+        V3 Ta = ld3(s.wr[c.bank(g)]), Fa = ld3(s.wr[c.bank(g)] + 3);
+        V3 Fh = ld3(s.wr[c.bhip(g)] + 3) + Fa;
+        V3 Th = ld3(s.wr[c.bhip(g)]) + Ta + cross(pa - ph, Fa);
+        float fl_h = s.ljar[2 * g] < 0.f ? -s.lD[2 * g] * s.ljar[2 * g] : 0.f;
+        float fl_a = s.ljar[2 * g + 1] < 0.f ? -s.lD[2 * g + 1] * s.ljar[2 * g + 1] : 0.f;
+        s.jtf[dh] = dot(ld3(s.axh[g]), Th) + s.lsgn[2 * g] * fl_h;
+        s.jtf[dh + 1] = dot(ld3(s.axa[g]), Ta) + s.lsgn[2 * g + 1] * fl_a;
+        st3(s.legF[g], Th); st3(s.legF[g] + 3, Fh);     // about the hip origin
+    }
+    RS_SYNC();
+    RS_LANE_LOOP(a, 2) {
+        V3 pt = ld3(s.org[a]);
+        V3 T = ld3(s.wr[a]), F = ld3(s.wr[a] + 3);
+        for (int l = 0; l < c.L(a); l++) {
+            int g = c.leg0(a) + l;
+            V3 Fg = ld3(s.legF[g] + 3);
+            T = T + ld3(s.legF[g]) + cross(ld3(s.org[c.bhip(g)]) - pt, Fg);
+            F = F + Fg;
+        }
+        V3 Tb = mulRT(s.Rt[a], T);
+        int va = c.vadr(a);
+        s.jtf[va] = F.x; s.jtf[va + 1] = F.y; s.jtf[va + 2] = F.z;
+        s.jtf[va + 3] = Tb.x; s.jtf[va + 4] = Tb.y; s.jtf[va + 5] = Tb.z;
+    }
+    RS_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------
+// H = M + J^T D_active J, assembled contact by contact
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+RS_HD void side_entry(const Ctx<LA, LB>& c, int b, int k, V3 p, V3 dir, int* idx, float* val) {
+    // k-th (0..7) dof of the chain of body b and the Jacobian entry of direction `dir` at point p
+    typedef Slab<LA, LB> S;
+    const S& s = *c.s;
+    *idx = -1; *val = 0.f;
+    if (b < 0) return;
+    int a, g = -1, depth = 0;
+    if (b < 2) a = b;
+    else if (b < 2 + S::LT) { g = b - 2; a = c.agent_of_leg(g); depth = 1; }
+    else { g = b - 2 - S::LT; a = c.agent_of_leg(g); depth = 2; }
+    int va = c.vadr(a);
+    if (k < 3) { *idx = va + k; *val = k == 0 ? dir.x : (k == 1 ? dir.y : dir.z); }
+    else if (k < 6) {
+        const float* R = s.Rt[a];
+        int e = k - 3;
+        V3 col = v3(R[e], R[3 + e], R[6 + e]);
+        *idx = va + k; *val = dot(col, cross(p - ld3(s.org[a]), dir));
+    } else if (k == 6 && depth >= 1) {
+        *idx = c.hipdof(g); *val = dot(ld3(s.axh[g]), cross(p - ld3(s.org[c.bhip(g)]), dir));
+    } else if (k == 7 && depth >= 2) {
+        *idx = c.hipdof(g) + 1; *val = dot(ld3(s.axa[g]), cross(p - ld3(s.org[c.bank(g)]), dir));
+    }
+}
+
+template <int LA, int LB>
+RS_HD void build_H(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NV * S::NVP) { s.H[i] = s.M[i]; }
+    RS_SYNC();
+    RS_LANE_LOOP(j, S::NU) {
+        if (s.ljar[j] < 0.f) { int dof = c.hipdof(j >> 1) + (j & 1); s.H[dof * S::NVP + dof] += s.lD[j]; }
+    }
+    int ncon = s.ncon;
+    for (int k = 0; k < ncon; k++) {
+        float a0 = s.cjar[k][0] < 0.f ? 1.f : 0.f, a1 = s.cjar[k][1] < 0.f ? 1.f : 0.f;
+        float a2 = s.cjar[k][2] < 0.f ? 1.f : 0.f, a3 = s.cjar[k][3] < 0.f ? 1.f : 0.f;
+        float na = a0 + a1 + a2 + a3;
+        if (na == 0.f) continue;       // uniform across the warp (shared data)
+        float D = s.cD[k];
+        float cnn = D * na, cn1 = RS_MU * D * (a0 - a1), c11 = RS_MU * RS_MU * D * (a0 + a1);
+        float cn2 = RS_MU * D * (a2 - a3), c22 = RS_MU * RS_MU * D * (a2 + a3);
+        float* sc = s.scr[k & 1];
+        RS_LANE_LOOP(e, 16) {
+            int side = e >> 3, kk = e & 7;
+            int b = side ? s.cbB[k] : s.cbA[k];
+            float sg = side ? 1.f : -1.f;
+            V3 p = ld3(s.cpos[k]);
+            int idx; float vn, v1, v2;
+            side_entry(c, b, kk, p, ld3(s.cfr[k]), &idx, &vn);
+            side_entry(c, b, kk, p, ld3(s.cfr[k] + 3), &idx, &v1);
+            side_entry(c, b, kk, p, ld3(s.cfr[k] + 6), &idx, &v2);
+            sc[e] = (float)idx; sc[16 + e] = sg * vn; sc[32 + e] = sg * v1; sc[48 + e] = sg * v2;
+        }
+        RS_SYNC();
+        int lo = s.cbA[k] < 0 ? 8 : 0;     // world side contributes nothing
+        int n = 16 - lo;
+        RS_LANE_LOOP(e, n * n) {
+            int r = lo + e / n, cc = lo + e % n;
+            int ir = (int)sc[r], ic = (int)sc[cc];
+            if (ir >= 0 && ic >= 0) {
+                float nr = sc[16 + r], nc = sc[16 + cc], t1r = sc[32 + r], t1c = sc[32 + cc], t2r = sc[48 + r], t2c = sc[48 + cc];
+                float val = cnn * nr * nc + cn1 * (nr * t1c + t1r * nc) + c11 * t1r * t1c + cn2 * (nr * t2c + t2r * nc) + c22 * t2r * t2c;
+                s.H[ir * S::NVP + ic] += val;
+            }
+        }
+        RS_SYNC();
+    }
+    RS_SYNC();
+}
+
+// in-place Cholesky H = L L^T (lower) and solve L L^T d = -g  (g in s.d on entry: gradient)
+template <int LA, int LB>
+RS_HD void chol_solve(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    const int n = S::NV, P = S::NVP;
+    for (int k = 0; k < n; k++) {
+        float dk = sqrtf(fmaxf(s.H[k * P + k], 1e-12f));
+        float inv = 1.f / dk;
+        RS_SYNC();
+        RS_LANE_LOOP(j, n) {
+            if (j > k) s.H[j * P + k] *= inv; else if (j == k) s.H[k * P + k] = dk;
+        }
+        RS_SYNC();
+        RS_LANE_LOOP(j, n) {
+            if (j > k) {
+                float ljk = s.H[j * P + k];
+                for (int cc = k + 1; cc <= j; cc++) s.H[j * P + cc] -= ljk * s.H[cc * P + k];
+            }
+        }
+        RS_SYNC();
+    }
+    RS_LANE_LOOP(j, n) { s.d[j] = -s.d[j]; }
+    RS_SYNC();
+    for (int k = 0; k < n; k++) {          // forward: L y = b
+        float yk = s.d[k] / s.H[k * P + k];
+        RS_SYNC();
+        RS_LANE_LOOP(j, n) { if (j > k) s.d[j] -= s.H[j * P + k] * yk; else if (j == k) s.d[k] = yk; }
+        RS_SYNC();
+    }
+    for (int k = n - 1; k >= 0; k--) {     // backward: L^T x = y
+        float xk = s.d[k] / s.H[k * P + k];
+        RS_SYNC();
+        RS_LANE_LOOP(j, n) { if (j < k) s.d[j] -= s.H[k * P + j] * xk; else if (j == k) s.d[k] = xk; }
+        RS_SYNC();
+    }
+}
+
+// out = M * vec (dense rows)
+template <int LA, int LB>
+RS_HD void mat_vec(Ctx<LA, LB>& c, const float* vec, float* out, const float* sub) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NV) {
+        float acc = 0.f;
+        for (int j = 0; j < S::NV; j++) acc += s.M[i * S::NVP + j] * vec[j];
+        out[i] = sub ? acc - sub[i] : acc;
+    }
+    RS_SYNC();
+}
+
+// phi'(alpha) and phi''(alpha) of the line search (uniform result)
+template <int LA, int LB>
+RS_HD void dphi(Ctx<LA, LB>& c, float alpha, float p0, float p1, float* d1, float* d2) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    int nc4 = 4 * s.ncon;
+    RS_LANE_LOOP(lane, 32) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = lane; i < nc4; i += 32) {
+            int k = i >> 2, r = i & 3;
+            float jd = s.cjd[k][r], j = s.cjar[k][r] + alpha * jd;
+            if (j < 0.f) { float D = s.cD[k]; a1 += D * j * jd; a2 += D * jd * jd; }
+        }
+        for (int i = lane; i < S::NU; i += 32) {
+            float jd = s.ljd[i], j = s.ljar[i] + alpha * jd;
+            if (s.lsgn[i] != 0.f && j < 0.f) { float D = s.lD[i]; a1 += D * j * jd; a2 += D * jd * jd; }
+        }
+        s.red[lane] = a1; s.red[32 + lane] = a2;
+    }
+    RS_SYNC();
+    float s1 = p0 + alpha * p1, s2 = p1;
+    for (int i = 0; i < 32; i++) { s1 += s.red[i]; s2 += s.red[32 + i]; }
+    RS_SYNC();
+    *d1 = s1; *d2 = s2;
+}
+
+template <int LA, int LB>
+RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
+    typedef Slab<LA, LB> S;
+    float acc = 0.f;
+    for (int i = 0; i < S::NV; i++) acc += a[i] * b[i];
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_fwdConstraint: primal Newton, exact line search, warm start from s.x
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+RS_HD void solve(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    twists(c, s.x);
+    rows_of(c, s.x, s.cjar, s.ljar);
+    RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] -= s.caref[k][r]; }
+    RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
+    mat_vec(c, s.x, s.r, s.tau);          // r = M x - tau  (syncs)
+    int it = 0;
+    for (; it < c.max_newton; it++) {
+        jt_forces(c);
+        RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
+        RS_SYNC();
+        build_H(c);
+        chol_solve(c);                                             // s.d = -H^-1 grad
+        twists(c, s.d);
+        rows_of(c, s.d, s.cjd, s.ljd);
+        mat_vec(c, s.d, s.Md, (const float*)0);
+        // does the active set survive the full step?
+        if (RS_LANE0) s.same = 1;
+        RS_SYNC();
+        RS_LANE_LOOP(k, s.ncon) {
+            for (int r = 0; r < 4; r++) if ((s.cjar[k][r] < 0.f) != (s.cjar[k][r] + s.cjd[k][r] < 0.f)) s.same = 0;
+        }
+        RS_LANE_LOOP(j, S::NU) {
+            if (s.lsgn[j] != 0.f && ((s.ljar[j] < 0.f) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
+        }
+        RS_SYNC();
+        int same = s.same;
+        float alpha = 1.f;
+        if (!same) {
+            float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
+            float lo = 0.f, hi = 1.f, d1, d2;
+            dphi(c, hi, p0, p1, &d1, &d2);
+            int guard = 0;
+            while (d1 < 0.f && guard < 8) { lo = hi; hi *= 2.f; dphi(c, hi, p0, p1, &d1, &d2); guard++; }
+            alpha = hi;
+            if (d1 > 0.f) {
+                for (int k = 0; k < 12; k++) {
+                    float an = alpha - d1 / d2;
+                    if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
+                    alpha = an;
+                    dphi(c, alpha, p0, p1, &d1, &d2);
+                    if (d1 < 0.f) lo = alpha; else hi = alpha;
+                    if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
+                }
+            }
+        }
+        RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; }
+        RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] += alpha * s.cjd[k][r]; }
+        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
+        RS_SYNC();
+        if (same) { it++; break; }
+    }
+    if (RS_LANE0) { s.niter = it; if (it >= c.max_newton) s.status |= RS_STATUS_NEWTON_MAXIT; }
+    RS_SYNC();
+}
+
+// one forward evaluation: qacc(q, v) into s.x
+template <int LA, int LB>
+RS_HD void forward(Ctx<LA, LB>& c) {
+    fk(c);
+    dynamics(c);
+    collide(c);
+    make_constraints(c);
+    solve(c);
+}
+
+// mj_integratePos from q0 with velocity vel over dt into s.q
+template <int LA, int LB>
+RS_HD void integrate_pos(Ctx<LA, LB>& c, const float* vel, float dt) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(a, 2) {
+        int qa = c.qadr(a), va = c.vadr(a);
+        for (int k = 0; k < 3; k++) s.q[qa + k] = s.q0[qa + k] + dt * vel[va + k];
+        V3 w = v3(vel[va + 3], vel[va + 4], vel[va + 5]);
+        float wn;
+        V3 ax = normalized(w, &wn);
+        float ang = dt * wn, sh, ch;
+        if (wn < 1e-12f) ang = 0.f;
+        sincosf(0.5f * ang, &sh, &ch);
+        float bw = ch, bx = sh * ax.x, by = sh * ax.y, bz = sh * ax.z;
+        float aw = s.q0[qa + 3], ax_ = s.q0[qa + 4], ay = s.q0[qa + 5], az = s.q0[qa + 6];
+        float w_ = aw*bw - ax_*bx - ay*by - az*bz, x_ = aw*bx + ax_*bw + ay*bz - az*by;
+        float y_ = aw*by - ax_*bz + ay*bw + az*bx, z_ = aw*bz + ax_*by - ay*bx + az*bw;
+        float n = sqrtf(w_*w_ + x_*x_ + y_*y_ + z_*z_), inv = n > 1e-12f ? 1.f / n : 1.f;
+        s.q[qa + 3] = w_ * inv; s.q[qa + 4] = x_ * inv; s.q[qa + 5] = y_ * inv; s.q[qa + 6] = z_ * inv;
+    }
+    RS_LANE_LOOP(g, S::LT) {
+        int qh = c.hipq(g), dh = c.hipdof(g);
+        s.q[qh] = s.q0[qh] + dt * vel[dh]; s.q[qh + 1] = s.q0[qh + 1] + dt * vel[dh + 1];
+    }
+    RS_SYNC();
+}
+
+// do_simulation: nsub x mj_step with RK4 (mujoco_env.py:125-129; mj_RungeKutta N=4)
+template <int LA, int LB>
+RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    const float h = c.h;
+    for (int sub = 0; sub < nsub; sub++) {
+        RS_LANE_LOOP(i, S::NQ) { s.q0[i] = s.q[i]; }
+        RS_LANE_LOOP(i, S::NV) { s.v0[i] = s.v[i]; s.vsum[i] = 0.f; s.asum[i] = 0.f; }
+        RS_SYNC();
+        for (int st = 0; st < 4; st++) {
+            forward(c);
+            if (st == 0) {   // mj_forward normalised qpos in place: carry that into the substep origin
+                RS_LANE_LOOP(a, 2) { for (int k = 3; k < 7; k++) s.q0[c.qadr(a) + k] = s.q[c.qadr(a) + k]; }
+            }
+            const float B = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
+            const float A = (st == 2) ? 1.f : 0.5f;
+            RS_LANE_LOOP(i, S::NV) { s.vsum[i] += B * s.v[i]; s.asum[i] += B * s.x[i]; }
+            RS_SYNC();
+            if (st < 3) {
+                integrate_pos(c, s.v, h * A);
+                RS_LANE_LOOP(i, S::NV) { s.v[i] = s.v0[i] + h * A * s.x[i]; }
+                RS_SYNC();
+            }
+        }
+        integrate_pos(c, s.vsum, h);
+        RS_LANE_LOOP(i, S::NV) { s.v[i] = s.v0[i] + h * s.asum[i]; }
+        RS_SYNC();
+    }
+}
+
+}  // namespace rs

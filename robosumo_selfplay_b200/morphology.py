@@ -101,7 +101,7 @@ class rs_agent_model(ctypes.Structure):
         ('L', ctypes.c_int), ('nq', ctypes.c_int), ('nv', ctypes.c_int), ('nu', ctypes.c_int),
         ('torso_r', ctypes.c_float), ('leg_r', ctypes.c_float), ('armature', ctypes.c_float),
         ('damping', ctypes.c_float), ('gear', ctypes.c_float), ('adjust_z', ctypes.c_float),
-        ('pad1', ctypes.c_float), ('pad2', ctypes.c_float),
+        ('reach', ctypes.c_float), ('pad2', ctypes.c_float),
         ('mT', ctypes.c_float), ('cT', ctypes.c_float * 3), ('IT', ctypes.c_float * 9),
         ('iw_torso', ctypes.c_float), ('iw_aux', ctypes.c_float * MAXL), ('iw_hip', ctypes.c_float * MAXL),
         ('iw_ank', ctypes.c_float * MAXL), ('iwd_hip', ctypes.c_float * MAXL), ('iwd_ank', ctypes.c_float * MAXL),
@@ -231,6 +231,8 @@ class AgentSpec:
         s.L, s.nq, s.nv, s.nu = self.L, self.nq, self.nv, self.nu
         s.torso_r, s.leg_r = self.torso_r, self.leg_r
         s.armature, s.damping, s.gear, s.adjust_z = HINGE_ARMATURE, HINGE_DAMPING, GEAR, self.adjust_z
+        s.reach = max(np.linalg.norm(self.r_hip[l]) + np.linalg.norm(self.r_ank[l]) + np.linalg.norm(self.e_ank[l])
+                      for l in range(self.L)) + max(self.leg_r, self.torso_r)
         s.mT = self.mT
         for k in range(3):
             s.cT[k] = self.cT[k]

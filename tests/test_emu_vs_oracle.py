@@ -1,0 +1,76 @@
+"""Kernel source (rs_core.h) compiled as a host emulation vs the independent double-precision oracle.
+CPU-only check of the math the CUDA kernels execute; the GPU parity tests are in test_gpu_*.py."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from robosumo_selfplay_b200.morphology import PairSpec
+from tests.emu.build import build
+from tests.helpers import reset_like_state, settled_states
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope='module')
+def emu():
+    return ctypes.CDLL(build())
+
+
+def emu_forward(L, ps, q, v, ctrl):
+    nv = ps.nv
+    q = np.array(q, np.float32); v = np.array(v, np.float32); ctrl = np.array(ctrl, np.float32)
+    qacc = np.zeros(nv, np.float32); M = np.zeros((nv, nv), np.float32); tau = np.zeros(nv, np.float32)
+    ncon, nit = ctypes.c_int(), ctypes.c_int()
+    st = L.emu_forward(ps.pack(), ctypes.c_float(0.01), 8, P(q), P(v), P(ctrl), P(qacc), P(M), P(tau),
+                       ctypes.byref(ncon), ctypes.byref(nit), None, None)
+    return qacc, M, ncon.value, nit.value, st
+
+
+@pytest.mark.parametrize('name', ['ant', 'bug', 'spider'])
+def test_free_flight_inertia_bias_limits(name, emu, oracle_models):
+    om = oracle_models(name); ps = PairSpec(name, name)
+    rng = np.random.RandomState(0)
+    for _ in range(4):
+        q, v = reset_like_state(om, rng, spread=2.0, z=3.0)
+        q[3:7] += rng.uniform(-.5, .5, 4); q[7:7 + 2 * ps.agents[0].L] += rng.uniform(-.6, .6, 2 * ps.agents[0].L)
+        v = rng.randn(om.nv) * 2.0
+        ctrl = rng.uniform(-1.5, 1.5, om.nu)
+        r = om.forward(q, v, ctrl, full=True)
+        qacc, M, ncon, nit, st = emu_forward(emu, ps, q, v, ctrl)
+        if r['ncon'] != 0:      # bug/spider legs can self-collide; intra-agent pairs are a later row
+            continue
+        assert ncon == 0
+        np.testing.assert_allclose(M, r['M'], atol=2e-6)
+        assert abs(qacc - r['qacc']).max() <= 1e-5 * abs(r['qacc']).max()
+
+
+def test_contact_forward_ant(emu, oracle_models):
+    om = oracle_models('ant'); ps = PairSpec('ant', 'ant')
+    rng = np.random.RandomState(5)
+    qs, vs = settled_states(om, rng, 6, steps=40, action_scale=0.15, spread=0.6)
+    seen = 0
+    for q, v in zip(qs, vs):
+        ctrl = rng.uniform(-1, 1, om.nu)
+        r = om.forward(q, v, ctrl, full=True)
+        qacc, M, ncon, nit, st = emu_forward(emu, ps, q, v, ctrl)
+        assert ncon == r['ncon'] and st == 0
+        seen += ncon
+        assert abs(qacc - r['qacc']).max() <= 2e-4 * max(1.0, abs(r['qacc']).max())
+    assert seen > 10
+
+
+def test_trajectory_ant_20_steps(emu, oracle_models):
+    om = oracle_models('ant'); ps = PairSpec('ant', 'ant')
+    rng = np.random.RandomState(7)
+    q, v = reset_like_state(om, rng)
+    qf, vf, wf = q.astype(np.float32), v.astype(np.float32), np.zeros(om.nv, np.float32)
+    w = np.zeros(om.nv)
+    for t in range(20):
+        ctrl = rng.randn(om.nu)
+        om.step(q, v, ctrl, 5, w)
+        st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 8, P(qf), P(vf), P(wf), P(ctrl.astype(np.float32)), 5)
+        assert st == 0
+        assert abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3, t
