@@ -97,6 +97,10 @@ int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_
  * qacc float[E][nv], ncon int[E], niter int[E] */
 int rs_forward_debug(rs_env* h, const float* ctrl, float* qacc, int* ncon, int* niter, void* stream);
 
+/* diagnostics of the last rs_step: int[E][3] = (Newton iterations, evaluations with an inter-agent contact,
+ * contacts) summed over the 20 forward evaluations of the step (cf. mjData.solver_iter / ncon) */
+int rs_get_diag(rs_env* h, int* diag, void* stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long rs_launch_count(void);
 

@@ -9,7 +9,7 @@ import os
 from .morphology import rs_agent_model
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librs_b200.so')
+LIB_PATH = os.environ.get('RS_B200_LIB', os.path.join(_HERE, 'librs_b200.so'))   # env override: kernel-variant experiments
 _lib = None
 
 c_void_p, c_int, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
@@ -35,6 +35,7 @@ SYMBOLS = {
     'rs_step': (c_int, [c_void_p] * 7 + [c_int, c_void_p]),
     'rs_step_host': (c_int, [c_void_p] * 7 + [c_int]),
     'rs_forward_debug': (c_int, [c_void_p] * 6),
+    'rs_get_diag': (c_int, [c_void_p] * 3),
 }
 
 

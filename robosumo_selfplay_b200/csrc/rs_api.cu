@@ -5,12 +5,27 @@
 #include <string.h>
 #include <atomic>
 #include <type_traits>
+#ifndef RS_WPB
+#define RS_WPB 15  // warps (env pairs) per block: 15 slabs of 14.7 KB = one block per SM
+#endif
+#ifndef RS_NO_LOCKSTEP
+#define RS_LOCKSTEP 1   // warps of a block re-align at every forward evaluation (instruction-cache locality)
+#endif
+#ifdef RS_LOCKSTEP
+#if defined(__CUDA_ARCH__)
+#define RS_EVAL_SYNC() __syncthreads()
+#ifdef RS_USE_PHASE_SYNC   /* measured slower than eval-level re-alignment alone (4.03 vs 3.49 ms/step, E=4096) */
+#define RS_PHASE_SYNC() __syncthreads()
+#define RS_BLOCK_ANY(p) __syncthreads_or(p)
+#endif
+#else
+#define RS_EVAL_SYNC()
+#endif
+#endif
 #include "rs_env.h"
 #include "rs_learn.cuh"
 
 using namespace rs;
-
-#define RS_WPB 5   // warps (env pairs) per block: 5 slabs of 14.7 KB -> 3 blocks = 15 warps per SM
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches(0);
@@ -23,7 +38,7 @@ static int fail(int code, const char* fmt, const char* detail) {
 struct EnvDev {
     int E;
     float *qpos, *qvel, *warm, *ep_ret, *ep_dret;
-    int *ep_step, *status;
+    int *ep_step, *status, *diag;      // diag[E][3]: Newton iterations, coupled evaluations, contacts summed over the last env step
     unsigned int* ep_count;
     const rs_agent_model* am;
     EnvParams P;
@@ -62,7 +77,7 @@ __device__ __forceinline__ void load_state(Ctx<LA, LB>& c, const EnvDev& d, int 
     RS_LANE_LOOP(i, S::NQ) { s.q[i] = d.qpos[(size_t)e * S::NQ + i]; }
     RS_LANE_LOOP(i, S::NV) { s.v[i] = d.qvel[(size_t)e * S::NV + i]; s.x[i] = d.warm[(size_t)e * S::NV + i]; }
     RS_LANE_LOOP(i, S::NV * S::NVP) { s.M[i] = 0.f; }
-    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; }
+    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; }
     RS_SYNC();
 }
 template <int LA, int LB>
@@ -141,7 +156,13 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
     int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+#ifdef RS_LOCKSTEP
+    const bool live = e < d.E;       // surplus warps of the last block shadow the last env (they must reach the block barriers)
+    if (!live) e = d.E - 1;
+#else
+    const bool live = true;
     if (e >= d.E) return;
+#endif
     S& s = *c.s;
     const int lane = threadIdx.x & 31;
     load_state(c, d, e);
@@ -162,6 +183,8 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     StepOut o;
     env_rewards(c, d.P, before, act, num_steps, d.h * d.P.frame_skip, &o);
     float er = d.ep_ret[e] + o.rew[0], edr = d.ep_dret[e] + o.info[0][6];
+    if (!live) return;
+    if (lane == 0) { d.diag[3 * e] = s.tot_iter; d.diag[3 * e + 1] = s.tot_coupled; d.diag[3 * e + 2] = s.tot_ncon; }
     if (lane == 0) {
         rew[2 * e] = o.rew[0]; rew[2 * e + 1] = o.rew[1];
         done[2 * e] = (uint8_t)o.done[0]; done[2 * e + 1] = (uint8_t)o.done[1];
@@ -192,11 +215,13 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_forward_debug(EnvDev d, const f
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
     int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
-    if (e >= d.E) return;
+    const bool live = e < d.E;
+    if (!live) e = d.E - 1;
     S& s = *c.s;
     load_state(c, d, e);
     set_act(c, ctrl + (size_t)e * S::NU);
     forward(c);
+    if (!live) return;
     RS_LANE_LOOP(i, S::NV) { qacc[(size_t)e * S::NV + i] = s.x[i]; }
     if (RS_LANE0) { ncon[e] = s.ncon; niter[e] = s.niter; }
 }
@@ -248,6 +273,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     CUDA_OK(cudaMalloc(&d.warm, sizeof(float) * E * h->nv)); CUDA_OK(cudaMalloc(&d.ep_ret, sizeof(float) * E));
     CUDA_OK(cudaMalloc(&d.ep_dret, sizeof(float) * E)); CUDA_OK(cudaMalloc(&d.ep_step, sizeof(int) * E));
     CUDA_OK(cudaMalloc(&d.status, sizeof(int) * E)); CUDA_OK(cudaMalloc(&d.ep_count, sizeof(unsigned int) * E));
+    CUDA_OK(cudaMalloc(&d.diag, sizeof(int) * E * 3)); CUDA_OK(cudaMemset(d.diag, 0, sizeof(int) * E * 3));
     CUDA_OK(cudaMemset(d.qpos, 0, sizeof(float) * E * h->nq)); CUDA_OK(cudaMemset(d.qvel, 0, sizeof(float) * E * h->nv));
     CUDA_OK(cudaMemset(d.warm, 0, sizeof(float) * E * h->nv)); CUDA_OK(cudaMemset(d.ep_ret, 0, sizeof(float) * E));
     CUDA_OK(cudaMemset(d.ep_dret, 0, sizeof(float) * E)); CUDA_OK(cudaMemset(d.ep_step, 0, sizeof(int) * E));
@@ -277,7 +303,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
 void rs_destroy(rs_env* h) {
     if (!h) return;
     cudaFree(h->d_am); cudaFree(h->d.qpos); cudaFree(h->d.qvel); cudaFree(h->d.warm); cudaFree(h->d.ep_ret);
-    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.status); cudaFree(h->d.ep_count);
+    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.diag); cudaFree(h->d.status); cudaFree(h->d.ep_count);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_epi); cudaFreeHost(h->h_done);
     cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_epi); cudaFree(h->s_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -353,6 +379,12 @@ int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_
     memcpy(obs, h->h_obs, sizeof(float) * E * OD); memcpy(rew, h->h_rew, sizeof(float) * E * 2); memcpy(done, h->h_done, E * 2);
     if (info) memcpy(info, h->h_info, sizeof(float) * E * 2 * RS_INFO_DIM);
     if (episode) memcpy(episode, h->h_epi, sizeof(float) * E * 3);
+    return RS_OK;
+}
+
+int rs_get_diag(rs_env* h, int* diag, void* stream) {
+    if (!h || !diag) return fail(RS_ERR_ARG, "rs_get_diag: bad argument%s", "");
+    CUDA_OK(cudaMemcpyAsync(diag, h->d.diag, sizeof(int) * h->d.E * 3, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return RS_OK;
 }
 

@@ -38,12 +38,14 @@
 #define RS_ATOMIC_ADDF(p, v) atomicAdd((p), (v))
 #define RS_ATOMIC_INC(p) atomicAdd((p), 1)
 #define RS_LANE0 ((threadIdx.x & 31) == 0)
+#define RS_RCP(x) __frcp_rn(x)
 #else
 #define RS_LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
 #define RS_SYNC()
 #define RS_ATOMIC_ADDF(p, v) (*(p) += (v))
 #define RS_ATOMIC_INC(p) ((*(p))++)
 #define RS_LANE0 (true)
+#define RS_RCP(x) (1.0f / (x))
 #endif
 
 #define RS_MAXCON 32
@@ -121,7 +123,8 @@ struct Slab {
     float lsgn[NU], lD[NU], laref[NU], ljar[NU], ljd[NU];
     float red[64];
     float scr[2][64];               // per-contact direction Jacobians: idx(16 as float) + 3 x 16
-    int ncon, status, niter, same;
+    int ncon, status, niter, same, coupled;
+    int tot_iter, tot_coupled, tot_ncon;      // diagnostics accumulated over one env step
 };
 
 template <int LA, int LB>
@@ -359,6 +362,7 @@ RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n,
     int k = RS_ATOMIC_INC(&s.ncon);
     if (k >= RS_MAXCON) return;    // counted, dropped: status flag raised by the caller
     s.cbA[k] = bA; s.cbB[k] = bB; s.cdist[k] = dist; s.ctran[k] = tran;
+    if (bA >= 0) s.coupled = 1;
     st3(s.cpos[k], pos);
     make_frame(n, yhint, s.cfr[k]);
 }
@@ -447,7 +451,7 @@ template <int LA, int LB>
 RS_HD void collide(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    if (RS_LANE0) s.ncon = 0;
+    if (RS_LANE0) { s.ncon = 0; s.coupled = 0; }
     RS_SYNC();
     // --- agent geoms against the world (floor plane, tatami box, four border rails) ---
     RS_LANE_LOOP(i, S::NG) {
@@ -731,42 +735,38 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
     RS_SYNC();
 }
 
-// in-place Cholesky H = L L^T (lower) and solve L L^T d = -g  (g in s.d on entry: gradient)
+// Solve  H d = -g  (g in s.d on entry) by Gauss-Jordan elimination without pivoting (H is SPD).
+// Row j lives with lane j (rows are smem-resident, stride NVP is odd -> conflict-free); every lane
+// eliminates the pivot column from its own row, rows above the pivot included, so there is no
+// back-substitution.  One warp barrier per pivot.  When no inter-agent contact couples the agents
+// H is block diagonal and both per-agent blocks are eliminated in the same pass (half the pivots,
+// half the columns).
 template <int LA, int LB>
 RS_HD void chol_solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    const int n = S::NV, P = S::NVP;
-    for (int k = 0; k < n; k++) {
-        float dk = sqrtf(fmaxf(s.H[k * P + k], 1e-12f));
-        float inv = 1.f / dk;
-        RS_SYNC();
-        RS_LANE_LOOP(j, n) {
-            if (j > k) s.H[j * P + k] *= inv; else if (j == k) s.H[k * P + k] = dk;
-        }
-        RS_SYNC();
-        RS_LANE_LOOP(j, n) {
-            if (j > k) {
-                float ljk = s.H[j * P + k];
-                for (int cc = k + 1; cc <= j; cc++) s.H[j * P + cc] -= ljk * s.H[cc * P + k];
+    const int P = S::NVP;
+    const bool bd = !s.coupled;
+    const int nk = bd ? (S::NVA > S::NV - S::NVA ? S::NVA : S::NV - S::NVA) : S::NV;
+    RS_LANE_LOOP(j, S::NV) { s.d[j] = -s.d[j]; }
+    RS_SYNC();
+    for (int k = 0; k < nk; k++) {
+        RS_LANE_LOOP(j, S::NV) {
+            const int b0 = (bd && j >= S::NVA) ? S::NVA : 0;
+            const int bn = bd ? (j >= S::NVA ? S::NV - S::NVA : S::NVA) : S::NV;
+            const int pk = b0 + k;
+            if (k < bn && j != pk) {
+                const float* prow = s.H + pk * P + b0;
+                float* jrow = s.H + j * P + b0;
+                float f = jrow[k] * RS_RCP(fmaxf(prow[k], 1e-12f));
+                for (int cc = k + 1; cc < bn; cc++) jrow[cc] = fmaf(-f, prow[cc], jrow[cc]);
+                s.d[j] = fmaf(-f, s.d[pk], s.d[j]);
             }
         }
         RS_SYNC();
     }
-    RS_LANE_LOOP(j, n) { s.d[j] = -s.d[j]; }
+    RS_LANE_LOOP(j, S::NV) { s.d[j] = s.d[j] * RS_RCP(fmaxf(s.H[j * P + j], 1e-12f)); }
     RS_SYNC();
-    for (int k = 0; k < n; k++) {          // forward: L y = b
-        float yk = s.d[k] / s.H[k * P + k];
-        RS_SYNC();
-        RS_LANE_LOOP(j, n) { if (j > k) s.d[j] -= s.H[j * P + k] * yk; else if (j == k) s.d[k] = yk; }
-        RS_SYNC();
-    }
-    for (int k = n - 1; k >= 0; k--) {     // backward: L^T x = y
-        float xk = s.d[k] / s.H[k * P + k];
-        RS_SYNC();
-        RS_LANE_LOOP(j, n) { if (j < k) s.d[j] -= s.H[k * P + j] * xk; else if (j == k) s.d[k] = xk; }
-        RS_SYNC();
-    }
 }
 
 // out = M * vec (dense rows)
@@ -819,25 +819,41 @@ RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
 // ------------------------------------------------------------------------------------------
 // mj_fwdConstraint: primal Newton, exact line search, warm start from s.x
 // ------------------------------------------------------------------------------------------
+#ifndef RS_PHASE_SYNC
+#define RS_PHASE_SYNC()          // optional block-wide re-alignment between phases (instruction-cache locality)
+#define RS_BLOCK_ANY(p) (p)
+#endif
 template <int LA, int LB>
 RS_HD void solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    twists(c, s.x);
-    rows_of(c, s.x, s.cjar, s.ljar);
-    RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] -= s.caref[k][r]; }
-    RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
-    mat_vec(c, s.x, s.r, s.tau);          // r = M x - tau  (syncs)
+    bool conv = false;
     int it = 0;
-    for (; it < c.max_newton; it++) {
-        jt_forces(c);
-        RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
-        RS_SYNC();
-        build_H(c);
-        chol_solve(c);                                             // s.d = -H^-1 grad
-        twists(c, s.d);
-        rows_of(c, s.d, s.cjd, s.ljd);
-        mat_vec(c, s.d, s.Md, (const float*)0);
+    // iteration -1 only evaluates the residuals at the warm start x0: jar = J x0 - aref, r = M x0 - tau
+    for (int iter = -1; iter < c.max_newton; iter++) {
+        if (!RS_BLOCK_ANY(!conv)) break;
+        const bool first = iter < 0;
+        if (!conv && !first) {
+            jt_forces(c);
+            RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
+            RS_SYNC();
+        }
+        RS_PHASE_SYNC();
+        if (!conv && !first) build_H(c);
+        RS_PHASE_SYNC();
+        if (!conv && !first) chol_solve(c);                            // s.d = -H^-1 grad
+        RS_PHASE_SYNC();
+        if (conv) continue;
+        const float* vec = first ? s.x : s.d;
+        twists(c, vec);
+        rows_of(c, vec, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
+        mat_vec(c, vec, first ? s.r : s.Md, first ? s.tau : (const float*)0);
+        if (first) {
+            RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] -= s.caref[k][r]; }
+            RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
+            RS_SYNC();
+            continue;
+        }
         // does the active set survive the full step?
         if (RS_LANE0) s.same = 1;
         RS_SYNC();
@@ -848,43 +864,49 @@ RS_HD void solve(Ctx<LA, LB>& c) {
             if (s.lsgn[j] != 0.f && ((s.ljar[j] < 0.f) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
         }
         RS_SYNC();
-        int same = s.same;
+        const int same = s.same;
         float alpha = 1.f;
         if (!same) {
-            float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
-            float lo = 0.f, hi = 1.f, d1, d2;
-            dphi(c, hi, p0, p1, &d1, &d2);
-            int guard = 0;
-            while (d1 < 0.f && guard < 8) { lo = hi; hi *= 2.f; dphi(c, hi, p0, p1, &d1, &d2); guard++; }
-            alpha = hi;
-            if (d1 > 0.f) {
-                for (int k = 0; k < 12; k++) {
-                    float an = alpha - d1 / d2;
-                    if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
-                    alpha = an;
-                    dphi(c, alpha, p0, p1, &d1, &d2);
-                    if (d1 < 0.f) lo = alpha; else hi = alpha;
-                    if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
-                }
+            // exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton inside a bracket
+            const float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
+            float lo = 0.f, hi = 0.f, d1, d2;
+            bool bracketed = false;
+            for (int k = 0; k < 20; k++) {
+                dphi(c, alpha, p0, p1, &d1, &d2);
+                if (d1 < 0.f) lo = alpha; else { hi = alpha; bracketed = true; }
+                if (!bracketed) { if (alpha >= 256.f) break; alpha *= 2.f; continue; }
+                if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
+                float an = alpha - d1 / d2;
+                if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
+                alpha = an;
             }
         }
         RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; }
         RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] += alpha * s.cjd[k][r]; }
         RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
         RS_SYNC();
-        if (same) { it++; break; }
+        it++;
+        if (same) conv = true;
     }
-    if (RS_LANE0) { s.niter = it; if (it >= c.max_newton) s.status |= RS_STATUS_NEWTON_MAXIT; }
+    if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled; s.tot_ncon += s.ncon; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
     RS_SYNC();
 }
 
 // one forward evaluation: qacc(q, v) into s.x
+#ifndef RS_EVAL_SYNC
+#define RS_EVAL_SYNC()
+#endif
 template <int LA, int LB>
 RS_HD void forward(Ctx<LA, LB>& c) {
+    RS_EVAL_SYNC();     // optional block-wide re-alignment of the warps (instruction-cache locality)
     fk(c);
+    RS_PHASE_SYNC();
     dynamics(c);
+    RS_PHASE_SYNC();
     collide(c);
+    RS_PHASE_SYNC();
     make_constraints(c);
+    RS_PHASE_SYNC();
     solve(c);
 }
 

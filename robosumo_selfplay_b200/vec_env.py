@@ -269,6 +269,13 @@ class B200SumoVecEnv(VecEnv):
                                             ctypes.c_void_p(ncon.data_ptr()), ctypes.c_void_p(nit.data_ptr()), self._stream()))
         return qacc, ncon, nit
 
+    def diagnostics(self):
+        """int32 [E, 3]: Newton iterations, coupled evaluations, contacts -- each summed over the last step's 20 evaluations."""
+        t = self.torch
+        out = t.empty((self.num_envs, 3), dtype=t.int32, device=self.device)
+        _lib.check(self._L.rs_get_diag(self._h, ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def check_status(self):
         """Raise like mujoco-py's warning callback does (builder.py:351-369) if any env went bad."""
         _, _, _, status = self.get_state()
