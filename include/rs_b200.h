@@ -97,6 +97,34 @@ int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_
  * qacc float[E][nv], ncon int[E], niter int[E] */
 int rs_forward_debug(rs_env* h, const float* ctrl, float* qacc, int* ncon, int* niter, void* stream);
 
+
+/* ---- learner side (device pointers, stream-ordered) ---------------------------------------------------------------
+ * Flat parameter vector = the reference checkpoint order (model.py:153-161 / tf.trainable_variables):
+ * pi.fc0.w[D,64] b pi.fc1.w[64,64] b vf.fc0.w[D,64] b vf.fc1.w[64,64] b pi.w[64,A] pi.b[A] logstd[1,A] vf.w[64,1] vf.b[1] */
+int rs_param_count(int obs_dim, int act_dim);
+/* PolicyWithValue mean / value heads (policies.py:84-128, models.py:93-101): mean [n,A] and/or value [n] (either may be NULL) */
+int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long obs_row_stride, int n,
+                   float* mean, float* value, void* stream);
+/* one rollout step of Runner.run (runner.py:62-100): sample a0 ~ pi0(o0), a1 ~ pi1(o1) and the four neglogps */
+int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* logstd1, const float* mu00, const float* mu10,
+                      const float* mu11, const float* mu01, unsigned long long seed, unsigned int tick, int deterministic,
+                      float* actions, float* nlp0, float* nlp1, float* opp_nlp0, float* opp_nlp1, void* stream);
+/* DiagGaussianPd.neglogp (distributions.py:238-241) */
+int rs_neglogp(int n, int act_dim, const float* act, const float* mu, const float* logstd, float* out, void* stream);
+/* V-trace returns and IS ratios (runner.py:166-200); arrays [2][T][E], last_values [2][E], last_dones [E][2], ratios [3][T][E] */
+int rs_vtrace(int T, int E, float gamma, float lam, float rho_bar, float c_bar, const float* rewards, const float* values,
+              const uint8_t* dones, const float* nlp, const float* opp_nlp, const float* last_values, const uint8_t* last_dones,
+              float* returns, float* ratios, void* stream);
+/* PPOModel.train (model.py:179-213), split so that a data-parallel caller can all-reduce between the pieces */
+int rs_adv_moments(const int* idx, int n, const float* returns, const float* values, double* sums, void* stream);
+long long rs_ppo_workspace_floats(int obs_dim, int act_dim, int max_minibatch);
+int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs, const float* actions, const float* returns,
+                const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
+                const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
+                float* log_ratio, void* stream);
+int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
+                 float lr, long long step_t, float beta1, float beta2, float eps, double* scratch, float* gnorm_out, void* stream);
+
 /* diagnostics of the last rs_step: int[E][3] = (Newton iterations, evaluations with an inter-agent contact,
  * contacts) summed over the 20 forward evaluations of the step (cf. mjData.solver_iter / ncon) */
 int rs_get_diag(rs_env* h, int* diag, void* stream);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 #include <atomic>
 #include <type_traits>
 #ifndef RS_WPB
@@ -396,6 +397,120 @@ int rs_forward_debug(rs_env* h, const float* ctrl, float* qacc, int* ncon, int* 
         CUDA_OK(cudaGetLastError());
         return RS_OK;
     });
+}
+
+
+// ------------------------------------------------------------------------------------------
+// learner-side entry points (rs_learn.cuh)
+// ------------------------------------------------------------------------------------------
+static int ensure_smem(const void* fn, size_t bytes) {
+    static std::atomic<size_t> cur_fwd(0), cur_ppo(0);
+    std::atomic<size_t>& cur = (fn == (const void*)rsl::k_mlp_forward) ? cur_fwd : cur_ppo;
+    if (bytes > cur.load()) {
+        CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur.store(bytes);
+    }
+    return RS_OK;
+}
+
+int rs_param_count(int obs_dim, int act_dim) { return rsl::make_layout(obs_dim, act_dim).P; }
+
+int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long ld, int n, float* mean, float* value, void* stream) {
+    if (!params || !obs || n <= 0 || act_dim > 8 || (!mean && !value)) return fail(RS_ERR_ARG, "rs_mlp_forward: bad argument%s", "");
+    size_t sm = rsl::tile_bytes(obs_dim, act_dim);
+    if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for one tile%s", "");
+    int rc = ensure_smem((const void*)rsl::k_mlp_forward, sm); if (rc) return rc;
+    rsl::k_mlp_forward<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* logstd1, const float* mu00, const float* mu10,
+                      const float* mu11, const float* mu01, unsigned long long seed, unsigned int tick, int deterministic,
+                      float* actions, float* nlp0, float* nlp1, float* opp_nlp0, float* opp_nlp1, void* stream) {
+    if (E <= 0 || act_dim > 16 || !actions) return fail(RS_ERR_ARG, "rs_rollout_sample: bad argument%s", "");
+    rsl::k_rollout_sample<<<(E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(E, act_dim, logstd0, logstd1, mu00, mu10, mu11, mu01, seed, tick,
+                                                                             deterministic, actions, nlp0, nlp1, opp_nlp0, opp_nlp1);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_neglogp(int n, int act_dim, const float* act, const float* mu, const float* logstd, float* out, void* stream) {
+    if (n <= 0 || act_dim > 16) return fail(RS_ERR_ARG, "rs_neglogp: bad argument%s", "");
+    rsl::k_neglogp<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, act_dim, act, mu, logstd, out);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_vtrace(int T, int E, float gamma, float lam, float rho_bar, float c_bar, const float* rewards, const float* values,
+              const uint8_t* dones, const float* nlp, const float* opp_nlp, const float* last_values, const uint8_t* last_dones,
+              float* returns, float* ratios, void* stream) {
+    if (T <= 0 || E <= 0 || !returns) return fail(RS_ERR_ARG, "rs_vtrace: bad argument%s", "");
+    rsl::k_vtrace<<<(2 * E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(T, E, gamma, lam, rho_bar, c_bar, rewards, values, dones, nlp, opp_nlp,
+                                                                        last_values, last_dones, returns, ratios);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_adv_moments(const int* idx, int n, const float* returns, const float* values, double* sums, void* stream) {
+    if (n < 0 || !sums) return fail(RS_ERR_ARG, "rs_adv_moments: bad argument%s", "");
+    CUDA_OK(cudaMemsetAsync(sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
+    if (n > 0) {
+        int blocks = (n + 255) / 256; if (blocks > 296) blocks = 296;
+        rsl::k_adv_moments<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, n, returns, values, sums);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+    }
+    return RS_OK;
+}
+
+long long rs_ppo_workspace_floats(int obs_dim, int act_dim, int max_minibatch) {
+    long long nb = (max_minibatch + RSL_TILE - 1) / RSL_TILE;
+    return nb * (rsl::make_layout(obs_dim, act_dim).P + 8) + 16;
+}
+
+/* local part of one PPO minibatch: grad_stats[P + 4] = sum over the n local samples of d loss / d theta (already divided by
+ * global_n) followed by the 4 stat sums (pg, vf, approxkl, clipfrac).  adv_sums[2] are the (global) advantage moments. */
+int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs, const float* actions, const float* returns,
+                const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
+                const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
+                float* log_ratio, void* stream) {
+    if (!params || !obs || !grad_stats || !workspace || act_dim > 8 || n < 0 || global_n <= 0) return fail(RS_ERR_ARG, "rs_ppo_grad: bad argument%s", "");
+    const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CUDA_OK(cudaMemsetAsync(grad_stats, 0, sizeof(float) * (L.P + 4), st)); return RS_OK; }
+    size_t sm = rsl::tile_bytes(obs_dim, act_dim);
+    if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_ppo_grad: obs_dim too large for one tile%s", "");
+    int rc = ensure_smem((const void*)rsl::k_ppo_tile, sm); if (rc) return rc;
+    const int nb = (n + RSL_TILE - 1) / RSL_TILE;
+    rsl::PPOArgs a;
+    a.params = params; a.D = obs_dim; a.A = act_dim; a.obs = obs; a.actions = actions; a.returns = returns; a.values = values;
+    a.old_nlp = old_nlp; a.weights = weights; a.idx = idx; a.n = n; a.adv_sums = adv_sums; a.adv_count = (double)global_n;
+    a.cliprange = cliprange; a.ent_coef = ent_coef; a.vf_coef = vf_coef; a.inv_n = 1.0f / (float)global_n;
+    a.gpart = workspace; a.spart = workspace + (size_t)nb * L.P; a.log_ratio = log_ratio;
+    rsl::k_ppo_tile<<<nb, RSL_TILE, sm, st>>>(a);
+    rsl::k_grad_reduce<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, grad_stats + L.P);
+    g_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
+/* entropy term, global-norm clip and TF-style Adam on the (all-reduced) gradient.  step_t counts from 1.  scratch: 2 doubles. */
+int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
+                 float lr, long long step_t, float beta1, float beta2, float eps, double* scratch, float* gnorm_out, void* stream) {
+    if (!params || !m || !v || !grad || !scratch || step_t < 1) return fail(RS_ERR_ARG, "rs_adam_step: bad argument%s", "");
+    const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    rsl::k_grad_finish<<<1, 1024, 0, st>>>(grad, L.P, ent_coef, act_dim, L.logstd, scratch);
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step_t)) / (1.0 - pow((double)beta1, (double)step_t));
+    rsl::k_adam<<<(L.P + 255) / 256, 256, 0, st>>>(params, m, v, grad, scratch, L.P, max_grad_norm, (float)lr_t, beta1, beta2, eps, gnorm_out);
+    g_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
 }
 
 }  // extern "C"

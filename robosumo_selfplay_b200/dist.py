@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed over NCCL (NVLink 5 / NVSwitch) on a box, gloo on CPU tests.
+
+Only two exchanges exist on this path: the flat gradient(+stats) all-reduce once per minibatch, with the
+3-scalar advantage-moment all-reduce in front of it, and the opponent-snapshot broadcast once per update.  Envs and their
+trajectories never leave the GPU that stepped them.  (The reference has no collective on this path; the vendored pattern
+this mirrors is MpiAdamOptimizer's flat all-reduce, baselines/baselines/common/mpi_adam_optimizer.py:21-46.)
+"""
+import os
+
+
+class Comm:
+    def __init__(self, backend=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if self.world > 1 and not dist.is_initialized():
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
+            kw = {}
+            if backend == 'nccl':
+                kw['device_id'] = torch.device('cuda', self.local_rank)
+            dist.init_process_group(backend, **kw)
+
+    def all_reduce_sum(self, tensor):
+        if self.world > 1:
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM)
+        return tensor
+
+    def broadcast(self, tensor, src=0):
+        if self.world > 1:
+            self.dist.broadcast(tensor, src=src)
+        return tensor
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def shard(self, n_global):
+        """Contiguous env range of this rank: [lo, hi)."""
+        per = n_global // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+
+def split_minibatch(global_idx, lo, hi):
+    """Part of a GLOBAL minibatch index slice that falls in this rank's sample range [lo, hi), as local indices.
+    Every rank replays the same host-side shuffle, so no sample moves between GPUs."""
+    import numpy as np
+    g = np.asarray(global_idx)
+    m = (g >= lo) & (g < hi)
+    return (g[m] - lo).astype(np.int32)

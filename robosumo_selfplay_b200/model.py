@@ -1,0 +1,139 @@
+"""PPOModel -- drop-in for the reference's model.py:9-213 (TF1 graph + session) on one B200.
+
+The learner parameters, Adam moments and all minibatch arithmetic stay on the device; `train` runs the hand-written
+kernels of csrc/rs_learn.cuh through the C ABI (rs_adv_moments -> rs_ppo_grad -> [NCCL all-reduce] -> rs_adam_step).
+Checkpoints are the reference's: `joblib.dump(list_of_13_float32_arrays)` in tf.trainable_variables order
+(model.py:153-177), so `/root/reference/model.ckpt`-style files load directly.
+"""
+import ctypes
+import os
+import types
+
+import numpy as np
+
+from . import _lib
+from .policies import PolicyWithValue, init_params, param_count, param_shapes, flatten_params, unflatten_params
+
+
+class PPOModel:
+    loss_names = ['policy_loss', 'value_loss', 'policy_entropy', 'approxkl', 'clipfrac']     # model.py:140
+
+    def __init__(self, *, ob_dim, ac_dim, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, trainable=True, model_scope="",
+                 device=0, max_minibatch=1 << 20, comm=None, policy=None, ob_space=None, ac_space=None, **_ignored):
+        import torch
+        self.torch = torch
+        self.D, self.A = ob_dim, ac_dim
+        self.P = param_count(ob_dim, ac_dim)
+        self.scope = model_scope
+        self.device = torch.device('cuda', device) if not isinstance(device, torch.device) else device
+        self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), max_grad_norm
+        self.trainable = trainable
+        self.comm = comm                        # robosumo_selfplay_b200.dist.Comm or None
+        self._L = _lib.lib()
+        assert self._L.rs_param_count(ob_dim, ac_dim) == self.P
+        self.params = torch.as_tensor(init_params(ob_dim, ac_dim), device=self.device)       # consumes np.random like ortho_init
+        self.act_model = PolicyWithValue(self.params, ob_dim, ac_dim, seed=abs(hash(model_scope)) % 9973)
+        self.train_model = types.SimpleNamespace(X=types.SimpleNamespace(dtype=types.SimpleNamespace(name='float32')))
+        self.step = self.act_model.step
+        self.value = self.act_model.value
+        self.initial_state = None
+        if trainable:
+            self.m = torch.zeros(self.P, dtype=torch.float32, device=self.device)
+            self.v = torch.zeros(self.P, dtype=torch.float32, device=self.device)
+            self.t = 0
+            self.grad_stats = torch.zeros(self.P + 4, dtype=torch.float32, device=self.device)
+            self.adv_sums = torch.zeros(2, dtype=torch.float64, device=self.device)
+            self.scratch = torch.zeros(2, dtype=torch.float64, device=self.device)
+            self.gnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._ws = None
+            self._ws_mb = 0
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _p(self, x):
+        return ctypes.c_void_p(x.data_ptr()) if x is not None else None
+
+    def _workspace(self, n):
+        if self._ws is None or n > self._ws_mb:
+            self._ws_mb = max(n, 1024)
+            self._ws = self.torch.empty(int(self._L.rs_ppo_workspace_floats(self.D, self.A, self._ws_mb)), dtype=self.torch.float32,
+                                        device=self.device)
+        return self._ws
+
+    def _dev(self, x, dtype=None):
+        t = self.torch
+        dtype = dtype or t.float32
+        if t.is_tensor(x):
+            return x.to(device=self.device, dtype=dtype).contiguous()
+        return t.as_tensor(np.ascontiguousarray(x), device=self.device).to(dtype).contiguous()
+
+    # ---- training ---------------------------------------------------------------------------
+    def train_indexed(self, lr, cliprange, obs, returns, actions, values, neglogpacs, weights, idx, global_n=None, want_log_ratio=False):
+        """One minibatch step on device-resident flat sample arrays; the minibatch is `idx` (int32 device tensor of LOCAL
+        sample indices).  With a communicator, every rank passes its local part of the global minibatch and `global_n`."""
+        t = self.torch
+        n = int(idx.numel()) if idx is not None else int(returns.numel())
+        gn = int(global_n) if global_n is not None else n
+        st = self._stream()
+        L = self._L
+        _lib.check(L.rs_adv_moments(self._p(idx), n, self._p(returns), self._p(values), self._p(self.adv_sums), st))
+        if self.comm is not None:
+            self.comm.all_reduce_sum(self.adv_sums)
+        log_ratio = t.empty(n, dtype=t.float32, device=self.device) if want_log_ratio else None
+        entropy = (self.act_model.logstd().double() + 0.5 * np.log(2.0 * np.pi * np.e)).sum()      # before the update (model.py:70)
+        _lib.check(L.rs_ppo_grad(self._p(self.params), self.D, self.A, self._p(obs), self._p(actions), self._p(returns), self._p(values),
+                                 self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(self.adv_sums), float(cliprange),
+                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio), st))
+        if self.comm is not None:
+            self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums]: one latency-bound NCCL all-reduce
+        self.t += 1
+        mgn = float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0
+        _lib.check(L.rs_adam_step(self._p(self.params), self._p(self.m), self._p(self.v), self._p(self.grad_stats), self.D, self.A,
+                                  self.ent_coef, mgn, float(lr), self.t, 0.9, 0.999, 1e-5, self._p(self.scratch), self._p(self.gnorm), st))
+        s4 = self.grad_stats[self.P:self.P + 4].double() / float(gn)
+        stats = t.stack([s4[0], s4[1], entropy, s4[2], s4[3]])           # device tensor in loss_names order
+        return stats, log_ratio
+
+    def stats_to_list(self, stats_dev):
+        return [float(x) for x in stats_dev.double().cpu().numpy()]
+
+    def train(self, lr, cliprange, obs, returns, masks, actions, values, neglogpacs, rewards, IS_weight, states=None):
+        """Reference signature (model.py:179-213): numpy minibatch in, [pg_loss, vf_loss, entropy, approxkl, clipfrac,
+        log_ratio, summary] out."""
+        obs_d = self._dev(obs); ret_d = self._dev(returns); act_d = self._dev(actions)
+        val_d = self._dev(values); nlp_d = self._dev(neglogpacs); w_d = self._dev(IS_weight)
+        stats, log_ratio = self.train_indexed(lr, cliprange, obs_d, ret_d, act_d, val_d, nlp_d, w_d, None, want_log_ratio=True)
+        return self.stats_to_list(stats) + [log_ratio.cpu().numpy(), None]
+
+    # ---- checkpoints (model.py:153-177) -----------------------------------------------------
+    def get_params_list(self):
+        return unflatten_params(self.params.cpu().numpy(), self.D, self.A)
+
+    def save(self, save_path):
+        import joblib
+        dirname = os.path.dirname(save_path)
+        if dirname:
+            os.makedirs(dirname, exist_ok=True)
+        joblib.dump(self.get_params_list(), save_path)
+
+    def load(self, load_path):
+        import joblib
+        loaded = joblib.load(os.path.expanduser(load_path))
+        self.load_list(loaded)
+
+    def load_list(self, loaded):
+        shapes = param_shapes(self.D, self.A)
+        if isinstance(loaded, dict):
+            loaded = [loaded[k] for k in sorted(loaded.keys())]
+        assert len(loaded) == len(shapes), 'number of variables loaded mismatches len(variables)'
+        for a, s in zip(loaded, shapes):
+            assert tuple(np.shape(a)) == tuple(s), (np.shape(a), s)
+        self.set_flat(flatten_params(loaded))
+
+    def set_flat(self, flat):
+        self.params.copy_(self.torch.as_tensor(np.asarray(flat, dtype=np.float32), device=self.device))
+
+    def get_flat(self):
+        return self.params.cpu().numpy().copy()

@@ -1,0 +1,169 @@
+"""GPU parity of the learner-side kernels (through the C ABI) against the CPU oracle and against the golden vectors
+produced by the reference's own runner.py (tests/golden/runner_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+D, A = 121, 8
+
+
+def test_mlp_forward_and_neglogp_match_oracle():
+    """PolicyWithValue heads: |mean|,|value| err <= 2e-5 abs on O(1) outputs; neglogp rel 1e-5; ragged n, strided rows."""
+    import torch
+    from oracle import ppo_oracle as po
+    from robosumo_selfplay_b200.model import PPOModel
+    np.random.seed(3)
+    m = PPOModel(ob_dim=D, ac_dim=A)
+    flat = m.get_flat()
+    flat += 0.05 * np.random.randn(flat.size).astype(np.float32)           # non-zero biases / logstd
+    m.set_flat(flat)
+    for n in (1, 127, 128, 300):
+        obs2 = np.random.randn(n, 2, D).astype(np.float32)
+        x = torch.as_tensor(obs2, device='cuda')[:, 1, :]                  # strided rows
+        mean, val = m.act_model.forward(x)
+        rm, rv, ls = po.forward(flat, obs2[:, 1, :], D, A)
+        np.testing.assert_allclose(mean.cpu().numpy(), rm, atol=2e-5)
+        np.testing.assert_allclose(val.cpu().numpy(), rv, atol=2e-5)
+        act = np.random.randn(n, A).astype(np.float32)
+        nlp = m.act_model.action_probability(x, given_action=torch.as_tensor(act, device='cuda'))
+        np.testing.assert_allclose(nlp.cpu().numpy(), po.neglogp(act, rm, ls), rtol=2e-5)
+    a, v, s, nl = m.step(obs2[:, 0, :])                                     # numpy in -> numpy out
+    assert a.shape == (300, A) and v.shape == (300,) and s is None and nl.shape == (300,)
+    rm, rv, ls = po.forward(flat, obs2[:, 0, :], D, A)
+    np.testing.assert_allclose(nl, po.neglogp(a, rm, ls), rtol=2e-5)
+    np.testing.assert_allclose(m.value(obs2[:, 0, :]), rv, atol=2e-5)
+
+
+@pytest.mark.parametrize('case', ['a', 'b', 'c'])
+def test_vtrace_matches_reference_runner_golden(case):
+    """Curriculum, IS ratios, V-trace returns and the sf01/sf0 layout against the reference's runner.py output:
+    rewards / ratios rel 1e-6, returns within 1 float32 ulp of the value scale (1.3e-7 * max|x| * 2)."""
+    import torch
+    from robosumo_selfplay_b200.runner import Runner, sf01
+    g = np.load(os.path.join(GOLD, 'runner_%s.npz' % case))
+    update, ab, gamma, lam, rb, cb = g['params']
+    R = Runner.__new__(Runner)
+    R.torch = torch; R.device = torch.device('cuda'); R.gamma, R.lam, R.rho_bar, R.c_bar = gamma, lam, rb, cb
+    R.anneal_bound = int(ab)
+    from robosumo_selfplay_b200 import _lib
+    R._L = _lib.lib()
+    dev = lambda k, dt=torch.float32: torch.as_tensor(g[k], device='cuda').to(dt)
+    rew, ret, ratios = R.postprocess(int(update), dev('in_shaping', torch.float64), dev('in_main', torch.float64), dev('in_values'),
+                                     dev('in_nlp'), dev('in_opp_nlp'), dev('in_dones', torch.uint8), dev('in_last_values'),
+                                     dev('in_last_dones', torch.uint8))
+    np.testing.assert_allclose(sf01(rew).cpu().numpy(), g['rewards'], rtol=1e-6, atol=1e-6)
+    scale = abs(g['returns']).max()
+    np.testing.assert_allclose(sf01(ret).cpu().numpy(), g['returns'], rtol=0, atol=2.6e-7 * scale)
+    np.testing.assert_allclose(ratios[0].t().reshape(-1).cpu().numpy(), g['off_policy_ratio'], rtol=2e-6)
+    np.testing.assert_allclose(ratios[1].t().reshape(-1).cpu().numpy(), g['off_env_ratio'], rtol=2e-6)
+    np.testing.assert_allclose(ratios[2].t().reshape(-1).cpu().numpy(), g['ratio'], rtol=4e-6)
+    # flat layout of the trajectory arrays is env-major: index e * T + t
+    assert np.array_equal(sf01(dev('in_obs')).cpu().numpy(), g['obs'])
+    assert np.array_equal(sf01(dev('in_dones', torch.uint8)).cpu().numpy().astype(bool), g['dones'])
+
+
+@pytest.mark.parametrize('n,use_idx', [(128, False), (1000, True), (77, True)])
+def test_ppo_minibatch_step_matches_oracle(n, use_idx):
+    """PPOModel.train: 5 stats rel 1e-4 (abs 1e-6), gradient rel 2e-4 of its max, parameters after 3 Adam steps atol 2e-6."""
+    import torch
+    from oracle import ppo_oracle as po
+    from robosumo_selfplay_b200.model import PPOModel
+    rng = np.random.RandomState(n)
+    np.random.seed(n)
+    m = PPOModel(ob_dim=D, ac_dim=A, ent_coef=0.01)
+    flat = m.get_flat() + 0.02 * rng.randn(m.P).astype(np.float32)
+    m.set_flat(flat)
+    N = 1500
+    obs = rng.randn(N, D).astype(np.float32); act = rng.randn(N, A).astype(np.float32) * 0.5
+    ret = rng.randn(N).astype(np.float32) * 2; val = rng.randn(N).astype(np.float32)
+    rm, rv, ls = po.forward(flat, obs, D, A)
+    old = (po.neglogp(act, rm, ls) + 0.3 * rng.randn(N)).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, N).astype(np.float32)
+    idx = rng.permutation(N)[:n].astype(np.int32) if use_idx else np.arange(n, dtype=np.int32)
+    d = lambda x: torch.as_tensor(x, device='cuda')
+    of, om_, ov = flat.astype(np.float64), np.zeros(m.P), np.zeros(m.P)
+    for step in range(1, 4):
+        stats, log_ratio = m.train_indexed(1e-3, 0.2, d(obs), d(ret), d(act), d(val), d(old), d(w), d(idx) if use_idx else None if n == N else d(idx),
+                                           want_log_ratio=True)
+        got = m.stats_to_list(stats)
+        g_gpu = m.grad_stats[:m.P].cpu().numpy().astype(np.float64)
+        of_prev = of
+        of, om_, ov, ostats, olr, ograd, ognorm = po.ppo_train_step(of, om_, ov, step, D, A, obs[idx], ret[idx], act[idx], val[idx], old[idx], w[idx],
+                                                                     1e-3, 0.2, ent_coef=0.01)
+        for a_, b_ in zip(got, ostats):
+            assert abs(a_ - b_) <= 1e-4 * abs(b_) + 1e-6, (step, got, ostats)
+        np.testing.assert_allclose(log_ratio.cpu().numpy(), olr, atol=2e-5)
+        assert abs(g_gpu - ograd).max() <= 2e-4 * abs(ograd).max(), step
+        assert abs(float(m.gnorm.item()) - ognorm) <= 1e-4 * ognorm
+        np.testing.assert_allclose(m.get_flat(), of, atol=2e-6)
+        # keep the oracle on the fp32 trajectory so that errors do not compound through Adam's 1/sqrt(v)
+        of = m.get_flat().astype(np.float64)
+        om_ = m.m.cpu().numpy().astype(np.float64); ov = m.v.cpu().numpy().astype(np.float64)
+
+
+def test_reference_train_signature_and_checkpoint_roundtrip(tmp_path):
+    import joblib
+    from robosumo_selfplay_b200.model import PPOModel
+    np.random.seed(0)
+    m = PPOModel(ob_dim=D, ac_dim=A)
+    rng = np.random.RandomState(1)
+    n = 256
+    out = m.train(1e-3, 0.2, rng.randn(n, D), rng.randn(n), None, rng.randn(n, A), rng.randn(n), 8 + rng.randn(n), rng.randn(n), np.ones(n))
+    assert len(out) == 7 and out[5].shape == (n,) and m.loss_names[3] == 'approxkl'
+    p = str(tmp_path / 'ck' / '00001')
+    m.save(p)
+    loaded = joblib.load(p)
+    assert [a.shape for a in loaded] == [(121, 64), (64,), (64, 64), (64,), (121, 64), (64,), (64, 64), (64,), (64, 8), (8,), (1, 8), (64, 1), (1,)]
+    m2 = PPOModel(ob_dim=D, ac_dim=A, trainable=False)
+    m2.load(p)
+    assert np.array_equal(m2.get_flat(), m.get_flat())
+
+
+def test_runner_and_learn_end_to_end_small():
+    """Runner.run on the device env: outputs are self-consistent with the policies; learn() runs 2 updates and its
+    minibatch schedule equals the NumPy legacy-RandomState replay of the reference's call order."""
+    import torch
+    from oracle import ppo_oracle as po
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200.runner import Runner
+    from robosumo_selfplay_b200 import alg_ppo
+    E, T = 64, 12
+    np.random.seed(5)
+    env = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E, seed=5, device_api=True)
+    models = [PPOModel(ob_dim=D, ac_dim=A), PPOModel(ob_dim=D, ac_dim=A, trainable=False)]
+    r = Runner(env=env, models=models, nsteps=T, gamma=0.995, lam=1.0, rho_bar=10.0, c_bar=1.0, anneal_bound=1000)
+    out = r.run(1)
+    obs, returns, dones, actions, values, nlp, rewards, opp_nlp, o_obs, o_act, states, epinfos, r1, r2, r3 = out
+    assert obs.shape == (2, E * T, D) and returns.shape == (2, E * T) and dones.dtype == bool and states is None
+    assert o_obs.shape == (T, E * D) and r3.shape == (E * T,)
+    np.testing.assert_allclose(models[0].value(obs[0]), values[0], atol=1e-5)
+    np.testing.assert_allclose(models[0].value(obs[1]), values[1], atol=1e-5)
+    np.testing.assert_allclose(models[0].act_model.action_probability(obs[1], given_action=actions[1]), nlp[1], rtol=1e-5)
+    np.testing.assert_allclose(models[1].act_model.action_probability(obs[0], given_action=actions[0]), opp_nlp[0], rtol=1e-5)
+    np.testing.assert_allclose(r3, np.exp(opp_nlp[1] - nlp[1]) * np.exp(nlp[0] - opp_nlp[0]), rtol=1e-5)
+    assert abs(obs[0][1, -1] - obs[0][0, -1] - 2 / 500) < 1e-6            # env-major flat index: e * T + t
+    env.close()
+    # learn(): record the minibatches actually trained on
+    seen = []
+    orig = PPOModel.train_indexed
+    def spy(self, lr, clip, obs, ret, act, val, nl, w, idx, **kw):
+        seen.append(idx.cpu().numpy().copy())
+        return orig(self, lr, clip, obs, ret, act, val, nl, w, idx, **kw)
+    PPOModel.train_indexed = spy
+    try:
+        env = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E, seed=7, device_api=True)
+        model = alg_ppo.learn(env=env, total_timesteps=2 * E * T, seed=11, nsteps=T, nminibatches=4, noptepochs=2, lr=1e-3, gamma=0.995, lam=1.0,
+                              rho_bar=10., c_bar=1., log_interval=1, anneal_bound=1000, opponent_mode='random')
+    finally:
+        PPOModel.train_indexed = orig
+    opp, sched = po.minibatch_schedule(11, D, A, 2, E * T, 4, 2, 'random')
+    flat = [mb for upd in sched for mb in upd]
+    assert len(seen) == len(flat) == 16
+    for a_, b_ in zip(seen, flat):
+        assert np.array_equal(a_, b_)                                      # bit-exact permutation
+    assert [h['opponent'] for h in model.history] == opp
+    assert np.isfinite(model.get_flat()).all()

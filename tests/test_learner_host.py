@@ -1,0 +1,101 @@
+"""CPU tests of the learner-side host logic: oracle vs the reference runner goldens, RNG stream / minibatch schedule,
+checkpoint format, minibatch sharding, and a world_size-2 gloo all-reduce of the flat gradient buffer."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.mark.parametrize('case', ['a', 'b', 'c'])
+def test_oracle_postprocess_matches_reference_runner(case):
+    from oracle.ppo_oracle import runner_postprocess, sf01, sf0
+    d = np.load(os.path.join(GOLD, 'runner_%s.npz' % case))
+    u, ab, g, l, rb, cb = d['params']
+    rew, ret, (op, oe, ra) = runner_postprocess(int(u), int(ab), g, l, rb, cb, d['in_shaping'], d['in_main'], d['in_values'], d['in_nlp'],
+                                                d['in_opp_nlp'], d['in_dones'], d['in_last_values'], d['in_last_dones'])
+    assert np.array_equal(sf01(rew), d['rewards']) and np.array_equal(sf0(ra), d['ratio']) and np.array_equal(sf0(op), d['off_policy_ratio'])
+    np.testing.assert_allclose(sf01(ret), d['returns'], rtol=0, atol=1.3e-7 * abs(d['returns']).max())
+    assert np.array_equal(sf01(d['in_dones']), d['dones']) and np.array_equal(sf01(d['in_values']), d['values'])
+
+
+def test_param_layout_and_rng_stream_match_oracle():
+    from oracle import ppo_oracle as po
+    from robosumo_selfplay_b200 import policies
+    assert policies.param_count(121, 8) == 24529 and policies.param_shapes(121, 8) == po.param_shapes(121, 8)
+    np.random.seed(42)
+    a = [policies.init_params(121, 8) for _ in range(3)]
+    c1 = np.random.choice(5, 1)[0]; s1 = np.arange(50); np.random.shuffle(s1)
+    np.random.seed(42)
+    b = [po.init_params(121, 8) for _ in range(3)]
+    c2 = np.random.choice(5, 1)[0]; s2 = np.arange(50); np.random.shuffle(s2)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert c1 == c2 and np.array_equal(s1, s2)
+    p = policies.unflatten_params(a[0], 121, 8)
+    w = p[0].astype(np.float64)
+    np.testing.assert_allclose(w.T @ w, 2.0 * np.eye(64), atol=1e-5)          # ortho_init scale sqrt(2)
+    assert abs(p[8]).max() < 0.01 and (p[10] == 0).all() and (p[1] == 0).all()
+    assert policies.logstd_offset(121, 8) == sum(int(np.prod(s)) for s in po.param_shapes(121, 8)[:10])
+
+
+def test_reference_checkpoint_format():
+    """model.ckpt of the reference (120-d obs vintage) has exactly our layout for D=120."""
+    import joblib
+    from robosumo_selfplay_b200 import policies
+    path = '/root/reference/model.ckpt'
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present on this box")
+    ck = joblib.load(path)
+    assert [tuple(a.shape) for a in ck] == policies.param_shapes(120, 8)
+    flat = policies.flatten_params(ck)
+    assert flat.size == policies.param_count(120, 8) == 24401
+    back = policies.unflatten_params(flat, 120, 8)
+    assert all(np.array_equal(x, y) for x, y in zip(back, ck))
+
+
+def test_minibatch_split_partitions_global_indices():
+    from robosumo_selfplay_b200.dist import split_minibatch
+    rng = np.random.RandomState(0)
+    N, world = 4096, 4
+    inds = rng.permutation(N)
+    for s in range(0, N, 512):
+        mb = inds[s:s + 512]
+        parts = [split_minibatch(mb, r * N // world, (r + 1) * N // world) + r * N // world for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == sorted(mb.tolist())
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    import torch
+    from robosumo_selfplay_b200.dist import Comm, split_minibatch
+    comm = Comm(backend='gloo')
+    # data-parallel minibatch: each rank sums "gradients" of its local part; the all-reduced flat buffer equals the global sum
+    N = 1024
+    rng = np.random.RandomState(7)
+    g_all = rng.randn(N, 5)
+    inds = rng.permutation(N)[:256]
+    lo, hi = comm.shard(N)
+    loc = split_minibatch(inds, lo, hi)
+    buf = torch.tensor(np.concatenate([g_all[lo:hi][loc].sum(0), [float(len(loc))]]))
+    comm.all_reduce_sum(buf)
+    snap = torch.full((4,), float(rank))
+    comm.broadcast(snap, 0)
+    q.put((rank, buf.numpy(), g_all[inds].sum(0), snap.numpy()))
+
+
+def test_gloo_world2_allreduce_and_broadcast():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    for rank, buf, want, snap in res:
+        np.testing.assert_allclose(buf[:5], want, rtol=1e-12)
+        assert buf[5] == 256 and (snap == 0).all()
