@@ -122,6 +122,73 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_learner(args, E, local, rank, world, dev):
+    """Secondary metrics of BASELINE.json: rollout steps/s (5 policy evaluations + physics per step, runner.py:62-104) and the
+    PPO2 update s/iter (V-trace + noptepochs x nminibatches minibatch steps on E*T samples per GPU, all-reduce when N > 1)."""
+    import numpy as np
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200.runner import Runner
+    from robosumo_selfplay_b200.dist import Comm, split_minibatch
+    from robosumo_selfplay_b200 import _lib
+    T, nmb, nep = args.nsteps, 32, 6
+    comm = Comm() if world > 1 else None
+    np.random.seed(0)
+    env = B200SumoVecEnv(ENV_ID, num_envs=E, seed=99 + rank, device=local, device_api=True)
+    models = [PPOModel(ob_dim=121, ac_dim=8, device=local, comm=comm), PPOModel(ob_dim=121, ac_dim=8, trainable=False, device=local)]
+    if comm is not None:
+        comm.broadcast(models[0].params, 0)
+    runner = Runner(env=env, models=models, nsteps=T, gamma=0.995, lam=1.0, rho_bar=10.0, c_bar=1.0, anneal_bound=1000)
+    runner.nsteps = 8
+    runner.run(1, as_numpy=False)                       # warm-up
+    runner.nsteps = T
+    torch.cuda.synchronize()
+    l0 = _lib.lib().rs_launch_count()
+    t0 = time.perf_counter()
+    R = runner.run(1, as_numpy=False)
+    torch.cuda.synchronize()
+    roll_s = time.perf_counter() - t0
+    roll_launches = _lib.lib().rs_launch_count() - l0
+    data = {k: R[k][0].contiguous() for k in ('obs', 'returns', 'actions', 'values', 'neglogpacs')}
+    N_local, N = E * T, E * T * world
+    nbt = N // nmb
+    lo, hi = rank * N_local, (rank + 1) * N_local
+    model = models[0]
+    def one_update():
+        inds = np.arange(N)
+        for ep in range(nep):
+            np.random.shuffle(inds)
+            if world == 1:
+                di = torch.as_tensor(inds.astype(np.int32), device=dev)
+                parts = [di[s0:s0 + nbt] for s0 in range(0, N, nbt)]
+            else:
+                loc = [split_minibatch(inds[s0:s0 + nbt], lo, hi) for s0 in range(0, N, nbt)]
+                cat = torch.as_tensor(np.concatenate(loc), device=dev); offs = np.cumsum([0] + [len(x) for x in loc])
+                parts = [cat[offs[i]:offs[i + 1]] for i in range(len(loc))]
+            for mb in parts:
+                model.train_indexed(1e-3, 0.2, data['obs'], data['returns'], data['actions'], data['values'], data['neglogpacs'], None, mb, global_n=nbt)
+    one_update()                                        # warm-up
+    torch.cuda.synchronize()
+    if comm is not None:
+        comm.barrier()
+    t0 = time.perf_counter()
+    one_update()
+    torch.cuda.synchronize()
+    upd_s = time.perf_counter() - t0
+    tt = torch.tensor([roll_s, upd_s], dtype=torch.float64, device=dev)
+    if comm is not None:
+        comm.all_reduce_sum(tt); tt /= world
+    roll_s, upd_s = float(tt[0]), float(tt[1])
+    flops = 114.6e3 * N * nep
+    return {'rollout': {'value': E * world * T / roll_s, 'unit': 'env-steps/s', 'T': T, 'launches_per_step': roll_launches / T,
+                        'note': 'Runner.run: 4 MLP launches + 1 sampling launch + 1 physics launch per step, no host sync'},
+            'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
+                           'higher_is_better': False, 'dtype': 'f32', 'achieved_tflops': flops / upd_s / 1e12,
+                           'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,
+                           'note': 'wall clock incl. host-side NumPy shuffles (bit-exact schedule) and the gradient all-reduce when N > 1'}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -132,6 +199,8 @@ def main():
     ap.add_argument('--settle', type=int, default=40, help='untimed steps before warm-up so contacts exist')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--no-learner', action='store_true', help='skip the rollout / PPO2-update secondary measurements')
+    ap.add_argument('--nsteps', type=int, default=128, help='T of the PPO2-update measurement (config 2: T in {128, 2048})')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -210,6 +279,9 @@ def main():
     e2e_value = E * world * n_e2e / float(e2e_t.item())
     h2d = a32.nbytes
     d2h = henv.h_obs.nbytes + henv.h_rew.nbytes + henv.h_done.nbytes + henv.h_info.nbytes + henv.h_epi.nbytes
+    learner = None
+    if not args.no_learner:
+        learner = measure_learner(args, E, local, rank, world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -248,6 +320,8 @@ def main():
         'clocks': clocks,
         'contact_full_envs': ncon_note,
     }
+    if learner is not None:
+        line['learner'] = learner
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
