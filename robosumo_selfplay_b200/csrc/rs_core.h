@@ -39,6 +39,10 @@
 #define RS_ATOMIC_INC(p) atomicAdd((p), 1)
 #define RS_LANE0 ((threadIdx.x & 31) == 0)
 #define RS_RCP(x) __frcp_rn(x)
+#define RS_RSQRT(x) (1.0f / sqrtf(x))      /* fast intrinsics (rsqrtf, __sincosf, __fdividef) were measured: no speed-up, parity loss */
+#define RS_SINCOS(x, s, c) sincosf((x), (s), (c))
+#define RS_DIV(a, b) ((a) / (b))
+#define RS_UNROLL1 _Pragma("unroll 1")
 #else
 #define RS_LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
 #define RS_SYNC()
@@ -46,6 +50,10 @@
 #define RS_ATOMIC_INC(p) ((*(p))++)
 #define RS_LANE0 (true)
 #define RS_RCP(x) (1.0f / (x))
+#define RS_RSQRT(x) (1.0f / sqrtf(x))
+#define RS_SINCOS(x, s, c) sincosf((x), (s), (c))
+#define RS_DIV(a, b) ((a) / (b))
+#define RS_UNROLL1
 #endif
 
 #define RS_MAXCON 32
@@ -79,10 +87,10 @@ RS_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RS_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 RS_HD float norm(V3 a) { return sqrtf(dot(a, a)); }
 RS_HD V3 normalized(V3 a, float* len) {
-    float n = norm(a);
-    *len = n;
-    if (n < 1e-12f) return v3(1.f, 0.f, 0.f);
-    float s = 1.f / n;
+    float d2 = dot(a, a);
+    if (d2 < 1e-24f) { *len = 0.f; return v3(1.f, 0.f, 0.f); }
+    float s = RS_RSQRT(d2);
+    *len = d2 * s;
     return s * a;
 }
 // R (row-major 3x3) * v  and  R^T * v
@@ -155,8 +163,8 @@ RS_HD void fk(Ctx<LA, LB>& c) {
     RS_LANE_LOOP(a, 2) {
         float* qq = s.q + c.qadr(a);
         float w = qq[3], x = qq[4], y = qq[5], z = qq[6];
-        float n = sqrtf(w * w + x * x + y * y + z * z);
-        if (n < 1e-12f) { w = 1.f; x = y = z = 0.f; } else { float inv = 1.f / n; w *= inv; x *= inv; y *= inv; z *= inv; }
+        float n2 = w * w + x * x + y * y + z * z;
+        if (n2 < 1e-24f) { w = 1.f; x = y = z = 0.f; } else { float inv = RS_RSQRT(n2); w *= inv; x *= inv; y *= inv; z *= inv; }
         qq[3] = w; qq[4] = x; qq[5] = y; qq[6] = z;
         float* R = s.Rt[a];
         R[0] = w*w + x*x - y*y - z*z; R[1] = 2.f*(x*y - w*z);         R[2] = 2.f*(x*z + w*y);
@@ -172,7 +180,7 @@ RS_HD void fk(Ctx<LA, LB>& c) {
         V3 pt = ld3(s.org[a]);
         float qh = s.q[c.hipq(g)], qa = s.q[c.hipq(g) + 1];
         float sh, ch, sa, ca;
-        sincosf(qh, &sh, &ch); sincosf(qa, &sa, &ca);
+        RS_SINCOS(qh, &sh, &ch); RS_SINCOS(qa, &sa, &ca);
         V3 axh = ld3(m.ax_hip[l]), axa = ld3(m.ax_ank[l]);
         V3 ph = pt + mulR(R, ld3(m.r_hip[l]));
         V3 pa = ph + mulR(R, rot(axh, sh, ch, ld3(m.r_ank[l])));
@@ -291,10 +299,10 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         // torso group in world axes about the torso origin
         V3 cT = mulR(R, ld3(m.cT));
         float IT[9];   // R IT R^T
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-            float acc = 0.f;
-            for (int p = 0; p < 3; p++) for (int q = 0; q < 3; q++) acc += R[3*i + p] * m.IT[3*p + q] * R[3*j + q];
-            IT[3*i + j] = acc;
+        {   // R IT R^T, IT symmetric: T = IT R^T (columns = IT applied to rows of R), then R T
+            V3 t0 = mulR(m.IT, v3(R[0], R[1], R[2])), t1 = mulR(m.IT, v3(R[3], R[4], R[5])), t2 = mulR(m.IT, v3(R[6], R[7], R[8]));
+            V3 c0 = mulR(R, t0), c1 = mulR(R, t1), c2 = mulR(R, t2);
+            IT[0] = c0.x; IT[3] = c0.y; IT[6] = c0.z; IT[1] = c1.x; IT[4] = c1.y; IT[7] = c1.z; IT[2] = c2.x; IT[5] = c2.y; IT[8] = c2.z;
         }
         float I10[10];
         float cc = dot(cT, cT);
@@ -378,7 +386,7 @@ RS_HD void sph_sph(Ctx<LA, LB>& c, int bA, int bB, V3 cA, float rA, V3 cB, float
 RS_HD V3 seg_nearest(V3 e0, V3 e1, V3 p) {
     V3 d = e1 - e0;
     float dd = dot(d, d);
-    float t = dd > 1e-20f ? dot(p - e0, d) / dd : 0.f;
+    float t = dd > 1e-20f ? RS_DIV(dot(p - e0, d), dd) : 0.f;
     t = fminf(fmaxf(t, 0.f), 1.f);
     return e0 + t * d;
 }
@@ -389,7 +397,8 @@ RS_HD void seg_seg(V3 p1, V3 a1, float l1, V3 p2, V3 a2, float l2, V3* o1, V3* o
     float det = 1.f - mb * mb;
     float x1, x2;
     if (fabsf(det) >= 1e-6f) {
-        x1 = (u - mb * v) / det; x2 = (v - mb * u) / det;
+        float idet = RS_RCP(det);
+        x1 = (u - mb * v) * idet; x2 = (v - mb * u) * idet;
         if (x1 > l1) { x1 = l1; x2 = v - mb * l1; } else if (x1 < -l1) { x1 = -l1; x2 = v + mb * l1; }
         if (x2 > l2) { x2 = l2; x1 = u - mb * l2; } else if (x2 < -l2) { x2 = -l2; x1 = u + mb * l2; }
         if (x1 > l1) x1 = l1; else if (x1 < -l1) x1 = -l1;
@@ -561,7 +570,7 @@ RS_HD void rows_of(Ctx<LA, LB>& c, const float* vec, float (*cout)[4], float* lo
 // constraint parameters (mj_makeConstraint + mj_makeImpedance): limits, pyramidal contacts
 // ------------------------------------------------------------------------------------------
 RS_HD float impedance(float pos_minus_margin) {
-    float x = fabsf(pos_minus_margin) / RS_WIDTH;
+    float x = fabsf(pos_minus_margin) * (1.0f / RS_WIDTH);
     float y;
     if (x >= 1.f) y = 1.f; else if (x <= 0.5f) y = 2.f * x * x; else y = 1.f - 2.f * (1.f - x) * (1.f - x);
     return RS_DMIN + y * (RS_DMAX - RS_DMIN);
@@ -776,6 +785,7 @@ RS_HD void mat_vec(Ctx<LA, LB>& c, const float* vec, float* out, const float* su
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NV) {
         float acc = 0.f;
+        RS_UNROLL1
         for (int j = 0; j < S::NV; j++) acc += s.M[i * S::NVP + j] * vec[j];
         out[i] = sub ? acc - sub[i] : acc;
     }
@@ -787,31 +797,42 @@ template <int LA, int LB>
 RS_HD void dphi(Ctx<LA, LB>& c, float alpha, float p0, float p1, float* d1, float* d2) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    int nc4 = 4 * s.ncon;
-    RS_LANE_LOOP(lane, 32) {
-        float a1 = 0.f, a2 = 0.f;
-        for (int i = lane; i < nc4; i += 32) {
-            int k = i >> 2, r = i & 3;
-            float jd = s.cjd[k][r], j = s.cjar[k][r] + alpha * jd;
-            if (j < 0.f) { float D = s.cD[k]; a1 += D * j * jd; a2 += D * jd * jd; }
-        }
-        for (int i = lane; i < S::NU; i += 32) {
-            float jd = s.ljd[i], j = s.ljar[i] + alpha * jd;
-            if (s.lsgn[i] != 0.f && j < 0.f) { float D = s.lD[i]; a1 += D * j * jd; a2 += D * jd * jd; }
-        }
-        s.red[lane] = a1; s.red[32 + lane] = a2;
+    const int nc4 = 4 * s.ncon;
+    const float* jar = &s.cjar[0][0]; const float* jdv = &s.cjd[0][0];
+#if defined(__CUDA_ARCH__)
+    float a1 = 0.f, a2 = 0.f;
+    RS_UNROLL1
+    for (int i = threadIdx.x & 31; i < nc4; i += 32) {
+        float jd = jdv[i], j = jar[i] + alpha * jd;
+        if (j < 0.f) { float D = s.cD[i >> 2]; a1 += D * j * jd; a2 += D * jd * jd; }
     }
-    RS_SYNC();
-    float s1 = p0 + alpha * p1, s2 = p1;
-    for (int i = 0; i < 32; i++) { s1 += s.red[i]; s2 += s.red[32 + i]; }
-    RS_SYNC();
-    *d1 = s1; *d2 = s2;
+    RS_UNROLL1
+    for (int i = threadIdx.x & 31; i < S::NU; i += 32) {
+        float jd = s.ljd[i], j = s.ljar[i] + alpha * jd;
+        if (s.lsgn[i] != 0.f && j < 0.f) { float D = s.lD[i]; a1 += D * j * jd; a2 += D * jd * jd; }
+    }
+    RS_UNROLL1
+    for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+    *d1 = p0 + alpha * p1 + a1; *d2 = p1 + a2;
+#else
+    float a1 = 0.f, a2 = 0.f;
+    for (int i = 0; i < nc4; i++) {
+        float jd = jdv[i], j = jar[i] + alpha * jd;
+        if (j < 0.f) { float D = s.cD[i >> 2]; a1 += D * j * jd; a2 += D * jd * jd; }
+    }
+    for (int i = 0; i < S::NU; i++) {
+        float jd = s.ljd[i], j = s.ljar[i] + alpha * jd;
+        if (s.lsgn[i] != 0.f && j < 0.f) { float D = s.lD[i]; a1 += D * j * jd; a2 += D * jd * jd; }
+    }
+    *d1 = p0 + alpha * p1 + a1; *d2 = p1 + a2;
+#endif
 }
 
 template <int LA, int LB>
 RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
     typedef Slab<LA, LB> S;
     float acc = 0.f;
+    RS_UNROLL1
     for (int i = 0; i < S::NV; i++) acc += a[i] * b[i];
     return acc;
 }
@@ -871,12 +892,13 @@ RS_HD void solve(Ctx<LA, LB>& c) {
             const float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
             float lo = 0.f, hi = 0.f, d1, d2;
             bool bracketed = false;
+            RS_UNROLL1
             for (int k = 0; k < 20; k++) {
                 dphi(c, alpha, p0, p1, &d1, &d2);
                 if (d1 < 0.f) lo = alpha; else { hi = alpha; bracketed = true; }
                 if (!bracketed) { if (alpha >= 256.f) break; alpha *= 2.f; continue; }
                 if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
-                float an = alpha - d1 / d2;
+                float an = alpha - RS_DIV(d1, d2);
                 if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
                 alpha = an;
             }
@@ -923,12 +945,12 @@ RS_HD void integrate_pos(Ctx<LA, LB>& c, const float* vel, float dt) {
         V3 ax = normalized(w, &wn);
         float ang = dt * wn, sh, ch;
         if (wn < 1e-12f) ang = 0.f;
-        sincosf(0.5f * ang, &sh, &ch);
+        RS_SINCOS(0.5f * ang, &sh, &ch);
         float bw = ch, bx = sh * ax.x, by = sh * ax.y, bz = sh * ax.z;
         float aw = s.q0[qa + 3], ax_ = s.q0[qa + 4], ay = s.q0[qa + 5], az = s.q0[qa + 6];
         float w_ = aw*bw - ax_*bx - ay*by - az*bz, x_ = aw*bx + ax_*bw + ay*bz - az*by;
         float y_ = aw*by - ax_*bz + ay*bw + az*bx, z_ = aw*bz + ax_*by - ay*bx + az*bw;
-        float n = sqrtf(w_*w_ + x_*x_ + y_*y_ + z_*z_), inv = n > 1e-12f ? 1.f / n : 1.f;
+        float n2 = w_*w_ + x_*x_ + y_*y_ + z_*z_, inv = n2 > 1e-24f ? RS_RSQRT(n2) : 1.f;
         s.q[qa + 3] = w_ * inv; s.q[qa + 4] = x_ * inv; s.q[qa + 5] = y_ * inv; s.q[qa + 6] = z_ * inv;
     }
     RS_LANE_LOOP(g, S::LT) {
