@@ -59,6 +59,7 @@ struct rs_env {
     uint8_t* s_done;
     cudaStream_t stream;
     size_t smem;
+    int wpb;      // warps (env pairs) per block: as many slabs as fit in one SM's shared memory, at most RS_WPB
 };
 
 template <int LA, int LB>
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_reset(EnvDev d, const uint8_t* 
     typedef Slab<LA, LB> S;
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
-    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= d.E) return;
     if (mask && !mask[e]) return;
     S& s = *c.s;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_set_state(EnvDev d, const float
     typedef Slab<LA, LB> S;
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
-    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= d.E) return;
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NQ) { s.q[i] = qpos[(size_t)e * S::NQ + i]; }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     typedef Slab<LA, LB> S;
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
-    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 #ifdef RS_LOCKSTEP
     const bool live = e < d.E;       // surplus warps of the last block shadow the last env (they must reach the block barriers)
     if (!live) e = d.E - 1;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_forward_debug(EnvDev d, const f
     typedef Slab<LA, LB> S;
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
-    int e = blockIdx.x * RS_WPB + (threadIdx.x >> 5);
+    int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const bool live = e < d.E;
     if (!live) e = d.E - 1;
     S& s = *c.s;
@@ -261,7 +262,10 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     h->obsB = agents[1].nq + agents[1].nv + 6 * (1 + 3 * agents[1].L) + 14;
     size_t sb = slab_bytes(h->LA, h->LB);
     if (!sb) { delete h; return fail(RS_ERR_UNSUPPORTED, "unsupported morphology pair%s", ""); }
-    h->smem = sb * RS_WPB;
+    h->wpb = (int)((227 * 1024 - 2 * sizeof(rs_agent_model) - 1024) / sb);
+    if (h->wpb > RS_WPB) h->wpb = RS_WPB;
+    if (h->wpb < 1) { delete h; return fail(RS_ERR_UNSUPPORTED, "slab does not fit in shared memory%s", ""); }
+    h->smem = sb * h->wpb;
     const int E = cfg->num_envs;
     CUDA_OK(cudaMalloc(&h->d_am, 2 * sizeof(rs_agent_model)));
     CUDA_OK(cudaMemcpy(h->d_am, agents, 2 * sizeof(rs_agent_model), cudaMemcpyHostToDevice));
@@ -319,7 +323,7 @@ int rs_dims(const rs_env* h, int* nq, int* nv, int* nu, int* obs_a, int* obs_b, 
     return RS_OK;
 }
 
-#define GRID(h) dim3(((h)->d.E + RS_WPB - 1) / RS_WPB), dim3(32 * RS_WPB), (h)->smem, (cudaStream_t)stream
+#define GRID(h) dim3(((h)->d.E + (h)->wpb - 1) / (h)->wpb), dim3(32 * (h)->wpb), (h)->smem, (cudaStream_t)stream
 
 int rs_reset(rs_env* h, const uint8_t* mask, float* obs, void* stream) {
     if (!h) return fail(RS_ERR_ARG, "rs_reset: null handle%s", "");

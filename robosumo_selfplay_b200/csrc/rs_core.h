@@ -370,7 +370,7 @@ RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n,
     int k = RS_ATOMIC_INC(&s.ncon);
     if (k >= RS_MAXCON) return;    // counted, dropped: status flag raised by the caller
     s.cbA[k] = bA; s.cbB[k] = bB; s.cdist[k] = dist; s.ctran[k] = tran;
-    if (bA >= 0) s.coupled = 1;
+    if (bA >= 0 && ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT)))) s.coupled = 1;
     st3(s.cpos[k], pos);
     make_frame(n, yhint, s.cfr[k]);
 }
@@ -512,6 +512,42 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                     else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
                     sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB);
                 }
+            }
+        }
+    }
+    // --- geoms of one agent against each other (mj_collision's parent/child and weld filters applied): only for the
+    //     six- and eight-legged bodies; the Ant's legs cannot reach each other (tests/test_oracle.py) ---
+    RS_UNROLL1
+    for (int a = 0; a < 2; a++) {
+        const int L = c.L(a);
+        if (L <= 4) continue;
+        const int npair = 2 * L * (L - 1), nank = L * (L + 1);      // 4 * C(L,2) leg-leg combinations, ankle vs torso group
+        RS_LANE_LOOP(p, npair + nank) {
+            int gi, gj;
+            if (p < npair) {
+                int pi = p >> 2, combo = p & 3, l = 0;
+                while (pi >= L - 1 - l) { pi -= L - 1 - l; l++; }
+                int m = l + 1 + pi;
+                gi = 2 + 3 * (c.leg0(a) + l) + 1 + (combo >> 1);
+                gj = 2 + 3 * (c.leg0(a) + m) + 1 + (combo & 1);
+            } else {
+                int q = p - npair, l = q / (L + 1), t = q - l * (L + 1);
+                gi = t == 0 ? a : 2 + 3 * (c.leg0(a) + t - 1);      // torso sphere or a welded stub capsule
+                gj = 2 + 3 * (c.leg0(a) + l) + 2;                   // ankle capsule
+            }
+            V3 a0, a1, b0, b1; float rA, rB, iwA, iwB; int bA, bB, agA, agB; bool sA, sB;
+            geom_of(c, gi, &a0, &a1, &rA, &bA, &iwA, &agA, &sA);
+            geom_of(c, gj, &b0, &b1, &rB, &bB, &iwB, &agB, &sB);
+            V3 ca = 0.5f * (a0 + a1), cb = 0.5f * (b0 + b1);
+            float la, lb;
+            V3 ua = normalized(a1 - a0, &la), ub = normalized(b1 - b0, &lb);
+            float bound = 0.5f * (la + lb) + rA + rB + RS_MARGIN;
+            V3 dc = cb - ca;
+            if (dot(dc, dc) < bound * bound) {
+                V3 pA, pB;
+                if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
+                else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
+                sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB);
             }
         }
     }
@@ -673,7 +709,7 @@ RS_HD void jt_forces(Ctx<LA, LB>& c) {
 // H = M + J^T D_active J, assembled contact by contact
 // ------------------------------------------------------------------------------------------
 template <int LA, int LB>
-RS_HD void side_entry(const Ctx<LA, LB>& c, int b, int k, V3 p, V3 dir, int* idx, float* val) {
+RS_HD void side_entry(const Ctx<LA, LB>& c, int b, int k, V3 p, V3 dir, bool skip_root, int* idx, float* val) {
     // k-th (0..7) dof of the chain of body b and the Jacobian entry of direction `dir` at point p
     typedef Slab<LA, LB> S;
     const S& s = *c.s;
@@ -684,6 +720,7 @@ RS_HD void side_entry(const Ctx<LA, LB>& c, int b, int k, V3 p, V3 dir, int* idx
     else if (b < 2 + S::LT) { g = b - 2; a = c.agent_of_leg(g); depth = 1; }
     else { g = b - 2 - S::LT; a = c.agent_of_leg(g); depth = 2; }
     int va = c.vadr(a);
+    if (k < 6 && skip_root) return;      // both bodies hang off the same floating base: root columns cancel exactly
     if (k < 3) { *idx = va + k; *val = k == 0 ? dir.x : (k == 1 ? dir.y : dir.z); }
     else if (k < 6) {
         const float* R = s.Rt[a];
@@ -722,9 +759,11 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
             float sg = side ? 1.f : -1.f;
             V3 p = ld3(s.cpos[k]);
             int idx; float vn, v1, v2;
-            side_entry(c, b, kk, p, ld3(s.cfr[k]), &idx, &vn);
-            side_entry(c, b, kk, p, ld3(s.cfr[k] + 3), &idx, &v1);
-            side_entry(c, b, kk, p, ld3(s.cfr[k] + 6), &idx, &v2);
+            const int bo = side ? s.cbA[k] : s.cbB[k];
+            const bool same = bo >= 0 && b >= 0 && ((bo < 2 ? bo : c.agent_of_leg((bo - 2) % S::LT)) == (b < 2 ? b : c.agent_of_leg((b - 2) % S::LT)));
+            side_entry(c, b, kk, p, ld3(s.cfr[k]), same, &idx, &vn);
+            side_entry(c, b, kk, p, ld3(s.cfr[k] + 3), same, &idx, &v1);
+            side_entry(c, b, kk, p, ld3(s.cfr[k] + 6), same, &idx, &v2);
             sc[e] = (float)idx; sc[16 + e] = sg * vn; sc[32 + e] = sg * v1; sc[48 + e] = sg * v2;
         }
         RS_SYNC();

@@ -40,9 +40,7 @@ def test_free_flight_inertia_bias_limits(name, emu, oracle_models):
         ctrl = rng.uniform(-1.5, 1.5, om.nu)
         r = om.forward(q, v, ctrl, full=True)
         qacc, M, ncon, nit, st = emu_forward(emu, ps, q, v, ctrl)
-        if r['ncon'] != 0:      # bug/spider legs can self-collide; intra-agent pairs are a later row
-            continue
-        assert ncon == 0
+        assert ncon == r['ncon']            # bug/spider legs may self-collide here: intra-agent pairs are part of the path
         np.testing.assert_allclose(M, r['M'], atol=2e-6)
         assert abs(qacc - r['qacc']).max() <= 1e-5 * abs(r['qacc']).max()
 
@@ -74,3 +72,21 @@ def test_trajectory_ant_20_steps(emu, oracle_models):
         st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 8, P(qf), P(vf), P(wf), P(ctrl.astype(np.float32)), 5)
         assert st == 0
         assert abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3, t
+
+
+@pytest.mark.parametrize('name', ['bug', 'spider'])
+def test_trajectory_bug_spider_with_self_collisions(name, emu, oracle_models):
+    """Six- and eight-legged bodies: intra-agent leg-leg contacts occur; 15 env steps stay within fp32 tolerance."""
+    om = oracle_models(name); ps = PairSpec(name, name)
+    rng = np.random.RandomState(1)
+    q, v = reset_like_state(om, rng)
+    qf, vf, wf = q.astype(np.float32), v.astype(np.float32), np.zeros(om.nv, np.float32)
+    w = np.zeros(om.nv)
+    seen = 0
+    for t in range(15):
+        ctrl = rng.randn(om.nu)
+        seen = max(seen, om.step(q, v, ctrl, 5, w))
+        st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 8, P(qf), P(vf), P(wf), P(ctrl.astype(np.float32)), 5)
+        assert st == 0
+        assert abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3, t
+    assert seen >= 2

@@ -101,3 +101,26 @@ def test_full_size_invariants_4096():
     assert torch.equal(obs[:, 0, 107:114], q[:, 15:22]) and torch.equal(obs[:, 1, 107:114], q[:, 0:7])
     want = (-1.0 + 2.0 * step.double() / 500.0).float()
     assert torch.equal(obs[:, 0, -1], want) and torch.equal(obs[:, 1, -1], want)
+
+
+@pytest.mark.parametrize('name,nq,nv,na', [('Bug', 38, 36, 12), ('Spider', 46, 44, 16)])
+def test_trajectory_parity_bug_spider(name, nq, nv, na, oracle_models):
+    """BASELINE config 3 morphologies (self-collisions included): 12 env steps, same tolerances as Ant."""
+    import torch
+    om = oracle_models(name.lower())
+    rng = np.random.RandomState(3)
+    E = 6
+    st = [reset_like_state(om, rng) for _ in range(E)]
+    q = np.array([s[0] for s in st]); v = np.array([s[1] for s in st]); w = np.zeros((E, om.nv))
+    env = make_env(E, name, device_api=True, auto_reset=False)
+    assert env.nq == nq and env.nv == nv and env.obs_dim == {'Bug': 165, 'Spider': 209}[name]
+    env.set_state(q, v)
+    for t in range(12):
+        a = rng.randn(E, 2, na)
+        env.step(torch.as_tensor(a, dtype=torch.float32, device='cuda'))
+        gq, gv, _, status = env.get_state()
+        for e in range(E):
+            om.step(q[e], v[e], a[e].ravel(), 5, w[e])
+        assert abs(gq.cpu().numpy() - q).max() < 2e-4, t
+        assert abs(gv.cpu().numpy() - v).max() < 5e-3, t
+        assert int((status & 7).max()) == 0
