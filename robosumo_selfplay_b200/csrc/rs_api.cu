@@ -7,7 +7,7 @@
 #include <atomic>
 #include <type_traits>
 #ifndef RS_WPB
-#define RS_WPB 15  // warps (env pairs) per block: 15 slabs of 14.7 KB = one block per SM
+#define RS_WPB 28  // max warps (env pairs) per block; one block per SM: 28 Ant slabs of 8.2 KB fill the 227 KB (E = 4096 -> one wave)
 #endif
 #ifndef RS_NO_LOCKSTEP
 #define RS_LOCKSTEP 1   // warps of a block re-align at every forward evaluation (instruction-cache locality)
@@ -78,7 +78,6 @@ __device__ __forceinline__ void load_state(Ctx<LA, LB>& c, const EnvDev& d, int 
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NQ) { s.q[i] = d.qpos[(size_t)e * S::NQ + i]; }
     RS_LANE_LOOP(i, S::NV) { s.v[i] = d.qvel[(size_t)e * S::NV + i]; s.x[i] = d.warm[(size_t)e * S::NV + i]; }
-    RS_LANE_LOOP(i, S::NV * S::NVP) { s.M[i] = 0.f; }
     if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; }
     RS_SYNC();
 }
@@ -262,7 +261,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     h->obsB = agents[1].nq + agents[1].nv + 6 * (1 + 3 * agents[1].L) + 14;
     size_t sb = slab_bytes(h->LA, h->LB);
     if (!sb) { delete h; return fail(RS_ERR_UNSUPPORTED, "unsupported morphology pair%s", ""); }
-    h->wpb = (int)((227 * 1024 - 2 * sizeof(rs_agent_model) - 1024) / sb);
+    h->wpb = (int)((227 * 1024 - 2 * sizeof(rs_agent_model)) / sb);
     if (h->wpb > RS_WPB) h->wpb = RS_WPB;
     if (h->wpb < 1) { delete h; return fail(RS_ERR_UNSUPPORTED, "slab does not fit in shared memory%s", ""); }
     h->smem = sb * h->wpb;

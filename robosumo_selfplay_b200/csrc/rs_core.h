@@ -56,7 +56,6 @@
 #define RS_UNROLL1
 #endif
 
-#define RS_MAXCON 32
 
 // scene constants (assets/tatami.xml, utils.py:64-88)
 #define RS_FLOOR_Z (-0.025f)
@@ -102,38 +101,55 @@ RS_HD V3 rot(V3 a, float s, float c, V3 v) { return c * v + s * cross(a, v) + ((
 template <int LA, int LB>
 struct Slab {
     enum {
-        LT = LA + LB, NQA = 7 + 2 * LA, NVA = 6 + 2 * LA, NQ = 14 + 2 * LT, NV = 12 + 2 * LT, NU = 2 * LT,
-        NVP = (NV | 1), NB = 2 + 2 * LT, NG = 2 + 3 * LT, NGA = 1 + 3 * LA, NGB = 1 + 3 * LB
+        LT = LA + LB, NQA = 7 + 2 * LA, NVA = 6 + 2 * LA, NVB = 6 + 2 * LB, NQ = 14 + 2 * LT, NV = 12 + 2 * LT, NU = 2 * LT,
+        NVP = (NV | 1), NB = 2 + 2 * LT, NG = 2 + 3 * LT, NGA = 1 + 3 * LA, NGB = 1 + 3 * LB,
+        MAXC = (LT <= 8 ? 24 : 32),                       // contact capacity per pair
+        // H storage: two per-agent blocks (row stride n+1) when the agents are uncoupled, one dense NV x NVP matrix when an
+        // inter-agent contact couples them.  The dense form spills over the arrays that are dead between build_H and the
+        // end of the linear solve (tw .. ljd below), so only HDED floats are dedicated to it.
+        BSA = NVA * (NVA + 1), BSB = NVB * (NVB + 1), HBD = BSA + BSB, HFULL = NV * NVP,
+        ALIAS = NB * 12 + LT * 6 + 2 * NV + MAXC * 4 + NU,
+        HDED = (HFULL - ALIAS > HBD ? HFULL - ALIAS : HBD)
     };
     float q[NQ], v[NV], q0[NQ], v0[NV], vsum[NV], asum[NV];
     float x[NV];      // qacc: Newton iterate, warm start across stages / steps
-    float tau[NV];    // qfrc_smooth = passive + actuator - bias
-    float r[NV];      // M x - tau
+    float r[NV];      // M x - qfrc_smooth  (dynamics() leaves -qfrc_smooth here, solve() adds M x)
     float d[NV];      // Newton direction
-    float Md[NV];
-    float jtf[NV];
     float act[NU];    // gear * clip(ctrl)
     float Rt[2][9];   // torso rotation matrices
     float org[NB][3]; // body origins: [a] torso a, [2+g] hip of leg g, [2+LT+g] ankle of leg g
     float tip[LT][3];
     float axh[LT][3], axa[LT][3];   // joint axes in world
-    float legI[LT][10];             // leg subtree spatial inertia about its torso origin: m, m*c, I(xx,xy,xz,yy,yz,zz)
-    float legF[LT][6];              // leg subtree (torque about torso origin / hip origin, force)
+    // joint-space inertia, arrowhead form: root 6x6 per agent, root-leg coupling 6x2 and leg 2x2 (hh, ha, aa) per leg
+    float Mr[2][36], Mc[LT][12], Ml[LT][3];
+    float H[HDED];
+    // ---- alias zone (order matters: the dense H extends over it) ----
     float tw[NB][6];                // body twists (omega, v at body origin)
     float wr[NB][6];                // body wrenches (torque about body origin, force)
-    float M[NV * NVP];
-    float H[NV * NVP];
-    // contacts
-    float cpos[RS_MAXCON][3], cfr[RS_MAXCON][9], cdist[RS_MAXCON], ctran[RS_MAXCON], cD[RS_MAXCON];
-    float caref[RS_MAXCON][4], cjar[RS_MAXCON][4], cjd[RS_MAXCON][4];
-    int cbA[RS_MAXCON], cbB[RS_MAXCON];
+    float legF[LT][6];              // leg subtree (torque, force)
+    float Md[NV];
+    float jtf[NV];
+    float cjd[MAXC][4];
+    float ljd[NU];
+    // ---- contacts: position, normal, first tangent (second = n x t1), D, rows ----
+    float cpos[MAXC][3], cn[MAXC][3], ct1[MAXC][3], cD[MAXC];
+    float caref[MAXC][4], cjar[MAXC][4];          // (dynamics() borrows these two as leg-inertia scratch)
+    int cbody[MAXC];                               // (bA + 1) | (bB + 1) << 8 ; -1 = world
     // joint limits (one potential row per hinge)
-    float lsgn[NU], lD[NU], laref[NU], ljar[NU], ljd[NU];
-    float red[64];
-    float scr[2][64];               // per-contact direction Jacobians: idx(16 as float) + 3 x 16
+    float lsgn[NU], lD[NU], laref[NU], ljar[NU];
+    float scr[64];                  // per-contact direction Jacobians: idx(16 as float) + 3 x 16
     int ncon, status, niter, same, coupled;
     int tot_iter, tot_coupled, tot_ncon;      // diagnostics accumulated over one env step
+    RS_HD float* legI(int g) { return &caref[0][0] + 10 * g; }
+    RS_HD int bA(int k) const { return (cbody[k] & 255) - 1; }
+    RS_HD int bB(int k) const { return (cbody[k] >> 8) - 1; }
+    // index of H(ir, ic); in block-diagonal mode ir and ic belong to the same agent
+    RS_HD int hidx(int ir, int ic) const {
+        if (coupled) return ir * NVP + ic;
+        return ir >= NVA ? BSA + (ir - NVA) * (NVB + 1) + (ic - NVA) : ir * (NVA + 1) + ic;
+    }
 };
+static_assert(2 * RS_MAXL * 10 <= 2 * 32 * 4, "leg inertia scratch must fit in caref + cjar");
 
 template <int LA, int LB>
 struct Ctx {
@@ -233,7 +249,6 @@ template <int LA, int LB>
 RS_HD void dynamics(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    const int NVP = S::NVP;
     RS_LANE_LOOP(g, S::LT) {
         int a = c.agent_of_leg(g), l = g - c.leg0(a);
         const rs_agent_model& m = c.am[a];
@@ -255,17 +270,14 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         float Maa = dot(axa, nA) + dot(sa_v, fA) + m.armature;
         float Mha = dot(axh, nA) + dot(sh_v, fA);
         float Mhh = dot(axh, nH) + dot(sh_v, fH) + m.armature;
-        s.M[da * NVP + da] = Maa; s.M[dh * NVP + da] = Mha; s.M[da * NVP + dh] = Mha; s.M[dh * NVP + dh] = Mhh;
+        s.Ml[g][0] = Mhh; s.Ml[g][1] = Mha; s.Ml[g][2] = Maa;
         V3 rA = mulRT(R, nA), rH = mulRT(R, nH);
         float colA[6] = { fA.x, fA.y, fA.z, rA.x, rA.y, rA.z }, colH[6] = { fH.x, fH.y, fH.z, rH.x, rH.y, rH.z };
-        for (int k = 0; k < 6; k++) {
-            s.M[(va + k) * NVP + da] = colA[k]; s.M[da * NVP + va + k] = colA[k];
-            s.M[(va + k) * NVP + dh] = colH[k]; s.M[dh * NVP + va + k] = colH[k];
-        }
+        for (int k = 0; k < 6; k++) { s.Mc[g][2 * k] = colH[k]; s.Mc[g][2 * k + 1] = colA[k]; }
         float I10[10];
         for (int k = 0; k < 10; k++) I10[k] = 0.f;
         accI(hip, I10); accI(ank, I10);
-        for (int k = 0; k < 10; k++) s.legI[g][k] = I10[k];
+        for (int k = 0; k < 10; k++) s.legI(g)[k] = I10[k];
         // ---- RNE with qacc = 0 ----
         const float* vv = s.v + va;
         V3 wt = mulR(R, v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
@@ -286,8 +298,8 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         float bias_a = dot(axa, nFa) + dot(sa_v, fFa);
         float bias_h = dot(axh, nFh) + dot(sh_v, fFh);
         int ua = (a ? 2 * LA : 0) + 2 * l;
-        s.tau[dh] = -m.damping * qdh + s.act[ua] - bias_h;
-        s.tau[da] = -m.damping * qda + s.act[ua + 1] - bias_a;
+        s.r[dh] = m.damping * qdh - s.act[ua] + bias_h;            // -qfrc_smooth
+        s.r[da] = m.damping * qda - s.act[ua + 1] + bias_a;
         s.legF[g][0] = nFh.x; s.legF[g][1] = nFh.y; s.legF[g][2] = nFh.z;
         s.legF[g][3] = fFh.x; s.legF[g][4] = fFh.y; s.legF[g][5] = fFh.z;
     }
@@ -312,23 +324,24 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         V3 nsum = v3(0, 0, 0), fsum = v3(0, 0, 0);
         for (int l = 0; l < c.L(a); l++) {
             int g = c.leg0(a) + l;
-            for (int k = 0; k < 10; k++) I10[k] += s.legI[g][k];
+            for (int k = 0; k < 10; k++) I10[k] += s.legI(g)[k];
             nsum = nsum + ld3(s.legF[g]); fsum = fsum + ld3(s.legF[g] + 3);
         }
         float mt = I10[0];
         V3 mc = v3(I10[1], I10[2], I10[3]);
         // root block: lin-lin m I ; lin-ang: column k = (R e_k) x mc ; ang-ang: R^T I_O R
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) s.M[(va + i) * S::NVP + va + j] = (i == j) ? mt : 0.f;
+        float* Mr = s.Mr[a];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Mr[i * 6 + j] = (i == j) ? mt : 0.f;
         float IO[9] = { I10[4], I10[5], I10[6], I10[5], I10[7], I10[8], I10[6], I10[8], I10[9] };
         for (int k = 0; k < 3; k++) {
             V3 ek = v3(R[k], R[3 + k], R[6 + k]);
             V3 f = cross(ek, mc);
             V3 n = mulR(IO, ek);
             V3 nb = mulRT(R, n);
-            s.M[(va + 0) * S::NVP + va + 3 + k] = f.x; s.M[(va + 3 + k) * S::NVP + va + 0] = f.x;
-            s.M[(va + 1) * S::NVP + va + 3 + k] = f.y; s.M[(va + 3 + k) * S::NVP + va + 1] = f.y;
-            s.M[(va + 2) * S::NVP + va + 3 + k] = f.z; s.M[(va + 3 + k) * S::NVP + va + 2] = f.z;
-            s.M[(va + 3) * S::NVP + va + 3 + k] = nb.x; s.M[(va + 4) * S::NVP + va + 3 + k] = nb.y; s.M[(va + 5) * S::NVP + va + 3 + k] = nb.z;
+            Mr[0 * 6 + 3 + k] = f.x; Mr[(3 + k) * 6 + 0] = f.x;
+            Mr[1 * 6 + 3 + k] = f.y; Mr[(3 + k) * 6 + 1] = f.y;
+            Mr[2 * 6 + 3 + k] = f.z; Mr[(3 + k) * 6 + 2] = f.z;
+            Mr[3 * 6 + 3 + k] = nb.x; Mr[4 * 6 + 3 + k] = nb.y; Mr[5 * 6 + 3 + k] = nb.z;
         }
         // torso group RNE
         const float* vv = s.v + va;
@@ -344,8 +357,8 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         V3 fT = af + cross(wt, hf);
         nT = nT + nsum; fT = fT + fsum;
         V3 nb = mulRT(R, nT);
-        s.tau[va + 0] = -fT.x; s.tau[va + 1] = -fT.y; s.tau[va + 2] = -fT.z;
-        s.tau[va + 3] = -nb.x; s.tau[va + 4] = -nb.y; s.tau[va + 5] = -nb.z;
+        s.r[va + 0] = fT.x; s.r[va + 1] = fT.y; s.r[va + 2] = fT.z;            // -qfrc_smooth (root: bias only)
+        s.r[va + 3] = nb.x; s.r[va + 4] = nb.y; s.r[va + 5] = nb.z;
     }
     RS_SYNC();
 }
@@ -353,13 +366,11 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
 // ------------------------------------------------------------------------------------------
 // collision (mj_collision restricted to the pairs this scene can produce)
 // ------------------------------------------------------------------------------------------
-RS_HD void make_frame(V3 n, V3 yhint, float* fr) {   // mju_makeFrame
+RS_HD V3 make_frame_y(V3 n, V3 yhint) {   // mju_makeFrame: second axis (third = n x second)
     V3 y = yhint;
     if (dot(y, y) < 0.25f) { y = (n.y < 0.5f && n.y > -0.5f) ? v3(0.f, 1.f, 0.f) : v3(0.f, 0.f, 1.f); }
     float len;
-    y = normalized(y - dot(n, y) * n, &len);
-    V3 z = cross(n, y);
-    st3(fr, n); st3(fr + 3, y); st3(fr + 6, z);
+    return normalized(y - dot(n, y) * n, &len);
 }
 
 template <int LA, int LB>
@@ -368,11 +379,12 @@ RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n,
     S& s = *c.s;
     if (!(dist < RS_MARGIN)) return;
     int k = RS_ATOMIC_INC(&s.ncon);
-    if (k >= RS_MAXCON) return;    // counted, dropped: status flag raised by the caller
-    s.cbA[k] = bA; s.cbB[k] = bB; s.cdist[k] = dist; s.ctran[k] = tran;
+    if (k >= S::MAXC) return;      // counted, dropped: status flag raised by the caller
+    s.cbody[k] = (bA + 1) | ((bB + 1) << 8);
+    s.cD[k] = dist; s.caref[k][0] = tran;      // parked here until make_constraints turns them into D and aref
     if (bA >= 0 && ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT)))) s.coupled = 1;
     st3(s.cpos[k], pos);
-    make_frame(n, yhint, s.cfr[k]);
+    st3(s.cn[k], n); st3(s.ct1[k], make_frame_y(n, yhint));
 }
 
 // sphere (centre cA, radius rA, side A) against sphere (cB, rB, side B): normal A -> B
@@ -552,7 +564,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
         }
     }
     RS_SYNC();
-    if (s.ncon > RS_MAXCON) { if (RS_LANE0) { s.ncon = RS_MAXCON; s.status |= RS_STATUS_CONTACT_FULL; } }
+    if (s.ncon > S::MAXC) { if (RS_LANE0) { s.ncon = S::MAXC; s.status |= RS_STATUS_CONTACT_FULL; } }
     RS_SYNC();
 }
 
@@ -591,8 +603,9 @@ RS_HD void rows_of(Ctx<LA, LB>& c, const float* vec, float (*cout)[4], float* lo
     S& s = *c.s;
     RS_LANE_LOOP(k, s.ncon) {
         V3 p = ld3(s.cpos[k]);
-        V3 rel = point_vel(s, s.cbB[k], p) - point_vel(s, s.cbA[k], p);
-        float un = dot(ld3(s.cfr[k]), rel), u1 = dot(ld3(s.cfr[k] + 3), rel), u2 = dot(ld3(s.cfr[k] + 6), rel);
+        V3 rel = point_vel(s, s.bB(k), p) - point_vel(s, s.bA(k), p);
+        V3 n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
+        float un = dot(n, rel), u1 = dot(t1, rel), u2 = dot(cross(n, t1), rel);
         cout[k][0] = un + RS_MU * u1; cout[k][1] = un - RS_MU * u1; cout[k][2] = un + RS_MU * u2; cout[k][3] = un - RS_MU * u2;
     }
     RS_LANE_LOOP(j, S::NU) {
@@ -637,9 +650,9 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
     rows_of(c, s.v, s.cjd, s.ljd);              // J v (scratch in cjd / ljd)
     RS_LANE_LOOP(j, S::NU) { s.laref[j] -= Bc * s.ljd[j]; }
     RS_LANE_LOOP(k, s.ncon) {
-        float pm = s.cdist[k] - RS_MARGIN;
+        float pm = s.cD[k] - RS_MARGIN;
         float imp = impedance(pm);
-        float diag = s.ctran[k] * (1.f + RS_MU * RS_MU);
+        float diag = s.caref[k][0] * (1.f + RS_MU * RS_MU);
         float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
         R = 2.f * RS_MU * RS_MU * R;
         s.cD[k] = 1.f / R;
@@ -662,10 +675,11 @@ RS_HD void jt_forces(Ctx<LA, LB>& c) {
         for (int r = 0; r < 4; r++) { float j = s.cjar[k][r]; f[r] = j < 0.f ? -D * j : 0.f; }
         float fn = f[0] + f[1] + f[2] + f[3];
         if (fn > 0.f) {
-            V3 F = fn * ld3(s.cfr[k]) + (RS_MU * (f[0] - f[1])) * ld3(s.cfr[k] + 3) + (RS_MU * (f[2] - f[3])) * ld3(s.cfr[k] + 6);
+            V3 cn_ = ld3(s.cn[k]), ct_ = ld3(s.ct1[k]);
+            V3 F = fn * cn_ + (RS_MU * (f[0] - f[1])) * ct_ + (RS_MU * (f[2] - f[3])) * cross(cn_, ct_);
             V3 p = ld3(s.cpos[k]);
             for (int side = 0; side < 2; side++) {
-                int b = side ? s.cbB[k] : s.cbA[k];
+                int b = side ? s.bB(k) : s.bA(k);
                 if (b < 0) continue;
                 V3 Fs = side ? F : (-1.f) * F;
                 V3 T = cross(p - ld3(s.org[b]), Fs);
@@ -738,12 +752,29 @@ template <int LA, int LB>
 RS_HD void build_H(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    RS_LANE_LOOP(i, S::NV * S::NVP) { s.H[i] = s.M[i]; }
+    float* H = s.H;
+    const int hn = s.coupled ? (int)S::HFULL : (int)S::HBD;
+    RS_LANE_LOOP(i, hn) { H[i] = 0.f; }
     RS_SYNC();
-    RS_LANE_LOOP(j, S::NU) {
-        if (s.ljar[j] < 0.f) { int dof = c.hipdof(j >> 1) + (j & 1); s.H[dof * S::NVP + dof] += s.lD[j]; }
+    // scatter the arrowhead inertia, one row per lane, and the active limit rows (diagonal)
+    RS_LANE_LOOP(i, S::NV) {
+        const int a = i >= S::NVA ? 1 : 0, va = c.vadr(a), k = i - va;
+        if (k < 6) {
+            for (int j = 0; j < 6; j++) H[s.hidx(i, va + j)] = s.Mr[a][k * 6 + j];
+            for (int l = 0; l < c.L(a); l++) {
+                const int g = c.leg0(a) + l, dh = va + 6 + 2 * l;
+                H[s.hidx(i, dh)] = s.Mc[g][2 * k]; H[s.hidx(i, dh + 1)] = s.Mc[g][2 * k + 1];
+            }
+        } else {
+            const int l = (k - 6) >> 1, isank = (k - 6) & 1, g = c.leg0(a) + l, dh = va + 6 + 2 * l, j = 2 * g + isank;
+            for (int kk = 0; kk < 6; kk++) H[s.hidx(i, va + kk)] = s.Mc[g][2 * kk + isank];
+            const float lim = s.ljar[j] < 0.f ? s.lD[j] : 0.f;
+            H[s.hidx(i, dh)] = isank ? s.Ml[g][1] : s.Ml[g][0] + lim;
+            H[s.hidx(i, dh + 1)] = isank ? s.Ml[g][2] + lim : s.Ml[g][1];
+        }
     }
-    int ncon = s.ncon;
+    RS_SYNC();
+    const int ncon = s.ncon;
     for (int k = 0; k < ncon; k++) {
         float a0 = s.cjar[k][0] < 0.f ? 1.f : 0.f, a1 = s.cjar[k][1] < 0.f ? 1.f : 0.f;
         float a2 = s.cjar[k][2] < 0.f ? 1.f : 0.f, a3 = s.cjar[k][3] < 0.f ? 1.f : 0.f;
@@ -752,22 +783,22 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
         float D = s.cD[k];
         float cnn = D * na, cn1 = RS_MU * D * (a0 - a1), c11 = RS_MU * RS_MU * D * (a0 + a1);
         float cn2 = RS_MU * D * (a2 - a3), c22 = RS_MU * RS_MU * D * (a2 + a3);
-        float* sc = s.scr[k & 1];
+        float* sc = s.scr;
+        const int bA = s.bA(k), bB = s.bB(k);
         RS_LANE_LOOP(e, 16) {
             int side = e >> 3, kk = e & 7;
-            int b = side ? s.cbB[k] : s.cbA[k];
+            int b = side ? bB : bA, bo = side ? bA : bB;
             float sg = side ? 1.f : -1.f;
-            V3 p = ld3(s.cpos[k]);
+            V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
             int idx; float vn, v1, v2;
-            const int bo = side ? s.cbA[k] : s.cbB[k];
             const bool same = bo >= 0 && b >= 0 && ((bo < 2 ? bo : c.agent_of_leg((bo - 2) % S::LT)) == (b < 2 ? b : c.agent_of_leg((b - 2) % S::LT)));
-            side_entry(c, b, kk, p, ld3(s.cfr[k]), same, &idx, &vn);
-            side_entry(c, b, kk, p, ld3(s.cfr[k] + 3), same, &idx, &v1);
-            side_entry(c, b, kk, p, ld3(s.cfr[k] + 6), same, &idx, &v2);
+            side_entry(c, b, kk, p, n, same, &idx, &vn);
+            side_entry(c, b, kk, p, t1, same, &idx, &v1);
+            side_entry(c, b, kk, p, cross(n, t1), same, &idx, &v2);
             sc[e] = (float)idx; sc[16 + e] = sg * vn; sc[32 + e] = sg * v1; sc[48 + e] = sg * v2;
         }
         RS_SYNC();
-        int lo = s.cbA[k] < 0 ? 8 : 0;     // world side contributes nothing
+        int lo = bA < 0 ? 8 : 0;       // world side contributes nothing
         int n = 16 - lo;
         RS_LANE_LOOP(e, n * n) {
             int r = lo + e / n, cc = lo + e % n;
@@ -775,7 +806,7 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
             if (ir >= 0 && ic >= 0) {
                 float nr = sc[16 + r], nc = sc[16 + cc], t1r = sc[32 + r], t1c = sc[32 + cc], t2r = sc[48 + r], t2c = sc[48 + cc];
                 float val = cnn * nr * nc + cn1 * (nr * t1c + t1r * nc) + c11 * t1r * t1c + cn2 * (nr * t2c + t2r * nc) + c22 * t2r * t2c;
-                s.H[ir * S::NVP + ic] += val;
+                H[s.hidx(ir, ic)] += val;
             }
         }
         RS_SYNC();
@@ -793,19 +824,18 @@ template <int LA, int LB>
 RS_HD void chol_solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    const int P = S::NVP;
     const bool bd = !s.coupled;
-    const int nk = bd ? (S::NVA > S::NV - S::NVA ? S::NVA : S::NV - S::NVA) : S::NV;
+    const int nk = bd ? (S::NVA > S::NVB ? S::NVA : S::NVB) : S::NV;
     RS_LANE_LOOP(j, S::NV) { s.d[j] = -s.d[j]; }
     RS_SYNC();
     for (int k = 0; k < nk; k++) {
         RS_LANE_LOOP(j, S::NV) {
             const int b0 = (bd && j >= S::NVA) ? S::NVA : 0;
-            const int bn = bd ? (j >= S::NVA ? S::NV - S::NVA : S::NVA) : S::NV;
+            const int bn = bd ? (j >= S::NVA ? S::NVB : S::NVA) : S::NV;
             const int pk = b0 + k;
             if (k < bn && j != pk) {
-                const float* prow = s.H + pk * P + b0;
-                float* jrow = s.H + j * P + b0;
+                const float* prow = s.H + s.hidx(pk, b0);       // pivot row, columns of this block
+                float* jrow = s.H + s.hidx(j, b0);
                 float f = jrow[k] * RS_RCP(fmaxf(prow[k], 1e-12f));
                 for (int cc = k + 1; cc < bn; cc++) jrow[cc] = fmaf(-f, prow[cc], jrow[cc]);
                 s.d[j] = fmaf(-f, s.d[pk], s.d[j]);
@@ -813,22 +843,50 @@ RS_HD void chol_solve(Ctx<LA, LB>& c) {
         }
         RS_SYNC();
     }
-    RS_LANE_LOOP(j, S::NV) { s.d[j] = s.d[j] * RS_RCP(fmaxf(s.H[j * P + j], 1e-12f)); }
+    RS_LANE_LOOP(j, S::NV) { s.d[j] = s.d[j] * RS_RCP(fmaxf(s.H[s.hidx(j, j)], 1e-12f)); }
     RS_SYNC();
 }
 
-// out = M * vec (dense rows)
+// out = M * vec (+ add) using the arrowhead structure of M
 template <int LA, int LB>
-RS_HD void mat_vec(Ctx<LA, LB>& c, const float* vec, float* out, const float* sub) {
+RS_HD void mat_vec(Ctx<LA, LB>& c, const float* vec, float* out, const float* add) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NV) {
-        float acc = 0.f;
-        RS_UNROLL1
-        for (int j = 0; j < S::NV; j++) acc += s.M[i * S::NVP + j] * vec[j];
-        out[i] = sub ? acc - sub[i] : acc;
+        const int a = i >= S::NVA ? 1 : 0, va = c.vadr(a), k = i - va;
+        float acc = add ? add[i] : 0.f;
+        if (k < 6) {
+            for (int j = 0; j < 6; j++) acc += s.Mr[a][k * 6 + j] * vec[va + j];
+            RS_UNROLL1
+            for (int l = 0; l < c.L(a); l++) {
+                const int g = c.leg0(a) + l;
+                acc += s.Mc[g][2 * k] * vec[va + 6 + 2 * l] + s.Mc[g][2 * k + 1] * vec[va + 7 + 2 * l];
+            }
+        } else {
+            const int l = (k - 6) >> 1, isank = (k - 6) & 1, g = c.leg0(a) + l;
+            for (int kk = 0; kk < 6; kk++) acc += s.Mc[g][2 * kk + isank] * vec[va + kk];
+            const float vh = vec[va + 6 + 2 * l], vk = vec[va + 7 + 2 * l];
+            acc += isank ? s.Ml[g][1] * vh + s.Ml[g][2] * vk : s.Ml[g][0] * vh + s.Ml[g][1] * vk;
+        }
+        out[i] = acc;
     }
     RS_SYNC();
+}
+// dense copy of M (tests / debugging)
+template <int LA, int LB>
+RS_HD void dense_M(Ctx<LA, LB>& c, float* out /*[NV*NV]*/) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    for (int i = 0; i < S::NV * S::NV; i++) out[i] = 0.f;
+    for (int a = 0; a < 2; a++) {
+        int va = c.vadr(a);
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) out[(va + i) * S::NV + va + j] = s.Mr[a][i * 6 + j];
+        for (int l = 0; l < c.L(a); l++) {
+            int g = c.leg0(a) + l, dh = va + 6 + 2 * l;
+            for (int k = 0; k < 6; k++) for (int w = 0; w < 2; w++) { out[(va + k) * S::NV + dh + w] = s.Mc[g][2 * k + w]; out[(dh + w) * S::NV + va + k] = s.Mc[g][2 * k + w]; }
+            out[dh * S::NV + dh] = s.Ml[g][0]; out[dh * S::NV + dh + 1] = s.Ml[g][1]; out[(dh + 1) * S::NV + dh] = s.Ml[g][1]; out[(dh + 1) * S::NV + dh + 1] = s.Ml[g][2];
+        }
+    }
 }
 
 // phi'(alpha) and phi''(alpha) of the line search (uniform result)
@@ -907,7 +965,7 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         const float* vec = first ? s.x : s.d;
         twists(c, vec);
         rows_of(c, vec, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
-        mat_vec(c, vec, first ? s.r : s.Md, first ? s.tau : (const float*)0);
+        mat_vec(c, vec, first ? s.r : s.Md, first ? s.r : (const float*)0);     // first: r = M x0 - qfrc_smooth
         if (first) {
             RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] -= s.caref[k][r]; }
             RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }

@@ -19,11 +19,11 @@ static int run_forward(const rs_agent_model* am, float h, int max_newton, const 
     }
     forward(c);
     memcpy(qacc, s->x, sizeof(float) * S::NV);
-    if (Mout) for (int i = 0; i < S::NV; i++) for (int j = 0; j < S::NV; j++) Mout[i * S::NV + j] = s->M[i * S::NVP + j];
-    if (tau) memcpy(tau, s->tau, sizeof(float) * S::NV);
+    if (Mout) dense_M(c, Mout);
+    if (tau) memset(tau, 0, sizeof(float) * S::NV);
     if (qnorm) memcpy(qnorm, s->q, sizeof(float) * S::NQ);
     *ncon = s->ncon; *niter = s->niter;
-    if (con) for (int k = 0; k < s->ncon; k++) { con[8*k] = s->cdist[k]; memcpy(con + 8*k + 1, s->cpos[k], 12); memcpy(con + 8*k + 4, s->cfr[k], 12); con[8*k+7] = (float)(s->cbA[k] * 100 + s->cbB[k]); }
+    if (con) for (int k = 0; k < s->ncon; k++) { con[8*k] = 0.f; memcpy(con + 8*k + 1, s->cpos[k], 12); memcpy(con + 8*k + 4, s->cn[k], 12); con[8*k+7] = (float)(s->bA(k) * 100 + s->bB(k)); }
     int st = s->status; free(s); return st;
 }
 
