@@ -102,9 +102,10 @@ int rs_forward_debug(rs_env* h, const float* ctrl, float* qacc, int* ncon, int* 
  * Flat parameter vector = the reference checkpoint order (model.py:153-161 / tf.trainable_variables):
  * pi.fc0.w[D,64] b pi.fc1.w[64,64] b vf.fc0.w[D,64] b vf.fc1.w[64,64] b pi.w[64,A] pi.b[A] logstd[1,A] vf.w[64,1] vf.b[1] */
 int rs_param_count(int obs_dim, int act_dim);
-/* PolicyWithValue mean / value heads (policies.py:84-128, models.py:93-101): mean [n,A] and/or value [n] (either may be NULL) */
+/* PolicyWithValue mean / value heads (policies.py:84-128, models.py:93-101): mean [n,A] and/or value [n] (either may be NULL).
+ * precision: 0 = FP32 pipe (numerics reference), 1 = tcgen05 tensor cores, tf32 inputs / fp32 accumulate */
 int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long obs_row_stride, int n,
-                   float* mean, float* value, void* stream);
+                   float* mean, float* value, int precision, void* stream);
 /* one rollout step of Runner.run (runner.py:62-100): sample a0 ~ pi0(o0), a1 ~ pi1(o1) and the four neglogps */
 int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* logstd1, const float* mu00, const float* mu10,
                       const float* mu11, const float* mu01, unsigned long long seed, unsigned int tick, int deterministic,
@@ -121,9 +122,13 @@ long long rs_ppo_workspace_floats(int obs_dim, int act_dim, int max_minibatch);
 int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs, const float* actions, const float* returns,
                 const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
                 const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
-                float* log_ratio, void* stream);
+                float* log_ratio, int precision, void* stream);
 int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
                  float lr, long long step_t, float beta1, float beta2, float eps, double* scratch, float* gnorm_out, void* stream);
+
+/* tcgen05 self-test (debug hook): D[128,64] = op(A)*op(B) with kind::tf32; prm13 = {a_rows,a_cols,b_rows,b_cols,a_mn,b_mn,
+ * a_lbo,a_sbo,a_step,b_lbo,b_sbo,b_step,nk} (bytes), host pointer */
+int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, void* stream);
 
 /* diagnostics of the last rs_step: int[E][3] = (Newton iterations, evaluations with an inter-agent contact,
  * contacts) summed over the 20 forward evaluations of the step (cf. mjData.solver_iter / ncon) */

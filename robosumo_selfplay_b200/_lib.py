@@ -36,15 +36,16 @@ SYMBOLS = {
     'rs_step_host': (c_int, [c_void_p] * 7 + [c_int]),
     'rs_forward_debug': (c_int, [c_void_p] * 6),
     'rs_get_diag': (c_int, [c_void_p] * 3),
+    'rs_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'rs_param_count': (c_int, [c_int, c_int]),
-    'rs_mlp_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
+    'rs_mlp_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'rs_rollout_sample': (c_int, [c_int, c_int] + [c_void_p] * 6 + [ctypes.c_ulonglong, ctypes.c_uint, c_int] + [c_void_p] * 6),
     'rs_neglogp': (c_int, [c_int, c_int] + [c_void_p] * 5),
     'rs_vtrace': (c_int, [c_int, c_int, c_float, c_float, c_float, c_float] + [c_void_p] * 10),
     'rs_adv_moments': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'rs_ppo_workspace_floats': (ctypes.c_longlong, [c_int, c_int, c_int]),
     'rs_ppo_grad': (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_int, ctypes.c_longlong, c_void_p, c_float, c_float, c_float,
-                            c_void_p, c_void_p, c_void_p, c_void_p]),
+                            c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'rs_adam_step': (c_int, [c_void_p] * 4 + [c_int, c_int, c_float, c_float, c_float, ctypes.c_longlong, c_float, c_float, c_float,
                              c_void_p, c_void_p, c_void_p]),
 }

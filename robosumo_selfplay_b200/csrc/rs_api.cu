@@ -12,19 +12,38 @@
 #ifndef RS_NO_LOCKSTEP
 #define RS_LOCKSTEP 1   // warps of a block re-align at every forward evaluation (instruction-cache locality)
 #endif
-#ifdef RS_LOCKSTEP
+// Re-alignment of the warps of a block (instruction-cache locality vs. waiting for the slowest warp):
+//   RS_SYNC_MODE 0 none, 1 every forward evaluation, 2 every substep (4 evaluations), 3 every evaluation within groups of
+//   RS_SYNC_GROUP warps (named barriers)
+#ifndef RS_SYNC_MODE
+#define RS_SYNC_MODE 1
+#endif
+#ifndef RS_SYNC_GROUP
+#define RS_SYNC_GROUP 7
+#endif
 #if defined(__CUDA_ARCH__)
+#if RS_SYNC_MODE == 1
 #define RS_EVAL_SYNC() __syncthreads()
-#ifdef RS_USE_PHASE_SYNC   /* measured slower than eval-level re-alignment alone (4.03 vs 3.49 ms/step, E=4096) */
+#elif RS_SYNC_MODE == 2
+#define RS_SUBSTEP_SYNC() __syncthreads()
+#elif RS_SYNC_MODE == 3
+#define RS_EVAL_SYNC() rs_group_sync()
+__device__ __forceinline__ void rs_group_sync() {
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5, g = w / RS_SYNC_GROUP;
+    const int first = g * RS_SYNC_GROUP, cnt = (nw - first < RS_SYNC_GROUP ? nw - first : RS_SYNC_GROUP) * 32;
+    asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "r"(cnt));
+}
+#endif
+#ifdef RS_USE_PHASE_SYNC
 #define RS_PHASE_SYNC() __syncthreads()
 #define RS_BLOCK_ANY(p) __syncthreads_or(p)
 #endif
-#else
-#define RS_EVAL_SYNC()
 #endif
-#endif
+#define RS_LOCKSTEP 1
 #include "rs_env.h"
 #include "rs_learn.cuh"
+#include "rs_tc.cuh"
+#include "rs_learn_tc.cuh"
 
 using namespace rs;
 
@@ -418,12 +437,21 @@ static int ensure_smem(const void* fn, size_t bytes) {
 
 int rs_param_count(int obs_dim, int act_dim) { return rsl::make_layout(obs_dim, act_dim).P; }
 
-int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long ld, int n, float* mean, float* value, void* stream) {
+int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long ld, int n, float* mean, float* value,
+                   int precision, void* stream) {
     if (!params || !obs || n <= 0 || act_dim > 8 || (!mean && !value)) return fail(RS_ERR_ARG, "rs_mlp_forward: bad argument%s", "");
-    size_t sm = rsl::tile_bytes(obs_dim, act_dim);
-    if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for one tile%s", "");
-    int rc = ensure_smem((const void*)rsl::k_mlp_forward, sm); if (rc) return rc;
-    rsl::k_mlp_forward<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
+    if (precision == 1) {
+        size_t sm = rsl::tc_tile_bytes(obs_dim);
+        if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for the tensor-core tile%s", "");
+        static std::atomic<size_t> cur(0);
+        if (sm > cur.load()) { CUDA_OK(cudaFuncSetAttribute(rsl::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cur.store(sm); }
+        rsl::k_mlp_forward_tc<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
+    } else {
+        size_t sm = rsl::tile_bytes(obs_dim, act_dim);
+        if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for one tile%s", "");
+        int rc = ensure_smem((const void*)rsl::k_mlp_forward, sm); if (rc) return rc;
+        rsl::k_mlp_forward<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
+    }
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
@@ -481,21 +509,27 @@ long long rs_ppo_workspace_floats(int obs_dim, int act_dim, int max_minibatch) {
 int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs, const float* actions, const float* returns,
                 const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
                 const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
-                float* log_ratio, void* stream) {
+                float* log_ratio, int precision, void* stream) {
     if (!params || !obs || !grad_stats || !workspace || act_dim > 8 || n < 0 || global_n <= 0) return fail(RS_ERR_ARG, "rs_ppo_grad: bad argument%s", "");
     const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { CUDA_OK(cudaMemsetAsync(grad_stats, 0, sizeof(float) * (L.P + 4), st)); return RS_OK; }
-    size_t sm = rsl::tile_bytes(obs_dim, act_dim);
+    size_t sm = precision == 1 ? rsl::tc_tile_bytes(obs_dim) : rsl::tile_bytes(obs_dim, act_dim);
     if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_ppo_grad: obs_dim too large for one tile%s", "");
-    int rc = ensure_smem((const void*)rsl::k_ppo_tile, sm); if (rc) return rc;
+    if (precision == 1) {
+        static std::atomic<size_t> cur(0);
+        if (sm > cur.load()) { CUDA_OK(cudaFuncSetAttribute(rsl::k_ppo_tile_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cur.store(sm); }
+    } else {
+        int rc = ensure_smem((const void*)rsl::k_ppo_tile, sm); if (rc) return rc;
+    }
     const int nb = (n + RSL_TILE - 1) / RSL_TILE;
     rsl::PPOArgs a;
     a.params = params; a.D = obs_dim; a.A = act_dim; a.obs = obs; a.actions = actions; a.returns = returns; a.values = values;
     a.old_nlp = old_nlp; a.weights = weights; a.idx = idx; a.n = n; a.adv_sums = adv_sums; a.adv_count = (double)global_n;
     a.cliprange = cliprange; a.ent_coef = ent_coef; a.vf_coef = vf_coef; a.inv_n = 1.0f / (float)global_n;
     a.gpart = workspace; a.spart = workspace + (size_t)nb * L.P; a.log_ratio = log_ratio;
-    rsl::k_ppo_tile<<<nb, RSL_TILE, sm, st>>>(a);
+    if (precision == 1) rsl::k_ppo_tile_tc<<<nb, RSL_TILE, sm, st>>>(a);
+    else rsl::k_ppo_tile<<<nb, RSL_TILE, sm, st>>>(a);
     rsl::k_grad_reduce<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, grad_stats + L.P);
     g_launches += 2;
     CUDA_OK(cudaGetLastError());
@@ -512,6 +546,22 @@ int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, in
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step_t)) / (1.0 - pow((double)beta1, (double)step_t));
     rsl::k_adam<<<(L.P + 255) / 256, 256, 0, st>>>(params, m, v, grad, scratch, L.P, max_grad_norm, (float)lr_t, beta1, beta2, eps, gnorm_out);
     g_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
+
+/* tcgen05 descriptor/layout self-test: D[128,64] = op(A) * op(B) through kind::tf32 UMMA (see rs_tc.cuh) */
+int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, void* stream) {
+    if (!prm13 || !A || !B || !D) return fail(RS_ERR_ARG, "rs_tc_selftest: bad argument%s", "");
+    rstc::SelfTestParams P;
+    for (int i = 0; i < 13; i++) P.v[i] = prm13[i];
+    if (P.v[0] * P.v[1] > 128 * 128 || P.v[2] * P.v[3] > 128 * 64) return fail(RS_ERR_ARG, "rs_tc_selftest: tile too large%s", "");
+    const size_t sm = sizeof(float) * (128 * 128 + 128 * 64);
+    static bool attr = false;
+    if (!attr) { CUDA_OK(cudaFuncSetAttribute(rstc::k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr = true; }
+    rstc::k_tc_selftest<<<1, 128, sm, (cudaStream_t)stream>>>(P, A, B, D);
+    g_launches++;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
 }

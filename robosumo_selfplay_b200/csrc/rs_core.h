@@ -1015,6 +1015,9 @@ RS_HD void solve(Ctx<LA, LB>& c) {
 #ifndef RS_EVAL_SYNC
 #define RS_EVAL_SYNC()
 #endif
+#ifndef RS_SUBSTEP_SYNC
+#define RS_SUBSTEP_SYNC()
+#endif
 template <int LA, int LB>
 RS_HD void forward(Ctx<LA, LB>& c) {
     RS_EVAL_SYNC();     // optional block-wide re-alignment of the warps (instruction-cache locality)
@@ -1064,6 +1067,7 @@ RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
     S& s = *c.s;
     const float h = c.h;
     for (int sub = 0; sub < nsub; sub++) {
+        RS_SUBSTEP_SYNC();
         RS_LANE_LOOP(i, S::NQ) { s.q0[i] = s.q[i]; }
         RS_LANE_LOOP(i, S::NV) { s.v0[i] = s.v[i]; s.vsum[i] = 0.f; s.asum[i] = 0.f; }
         RS_SYNC();

@@ -1,0 +1,324 @@
+// rs_learn_tc.cuh -- tensor-core (tcgen05, kind::tf32, TMEM accumulators) versions of the batched MLP kernels of
+// rs_learn.cuh: policy/value inference and the PPO2 minibatch forward/backward.
+//
+// Per 128-sample tile and per net, the three GEMMs whose operands are already K-contiguous run on the 5th-gen tensor cores:
+//     F1  H1pre[128,64] = X[128,K0] * W0[K0,64]      (K0 = D padded to a multiple of 8, zero filled)
+//     F2  H2pre[128,64] = H1[128,64] * W1[64,64]
+//     B2  dH1  [128,64] = dZ2[128,64] * W1^T
+// one elected thread issues tcgen05.mma, the accumulator lives in TMEM and comes back with tcgen05.ld as "thread t = sample
+// row t" for the bias / ReLU / mask epilogues.  The weight-gradient products (in^T * dz, K = the sample index) stay on the
+// FP32 pipe: their operands would need MN-major (transposed) descriptors, which this build does not use.
+// Operand tiles use the no-swizzle core-matrix layout of rs_tc.cuh.  Numerics: tf32 inputs (10-bit mantissa), fp32 accumulate.
+#pragma once
+#include "rs_learn.cuh"
+#include "rs_tc.cuh"
+
+namespace rsl {
+
+using rstc::tile_off;
+
+struct TcTile {
+    float *xs, *h1, *h2, *w0t, *w1t, *w1n, *b0, *b1, *wh, *bh, *dout;
+    int K0;
+};
+__host__ __device__ inline int tc_k0(int D) { return (D + 7) & ~7; }
+__host__ __device__ inline size_t tc_tile_bytes(int D) {
+    const int K0 = tc_k0(D);
+    return sizeof(float) * ((size_t)RSL_TILE * K0 + 2 * RSL_TILE * RSL_H + (size_t)RSL_H * K0 + 2 * RSL_H * RSL_H + 2 * RSL_H + RSL_H * 8 + 8 + RSL_TILE * 9) + 1024;
+}
+__device__ inline TcTile tc_carve(float* base, int D) {
+    TcTile t; t.K0 = tc_k0(D);
+    t.xs = base; base += RSL_TILE * t.K0;
+    t.h1 = base; base += RSL_TILE * RSL_H;
+    t.h2 = base; base += RSL_TILE * RSL_H;
+    t.w0t = base; base += RSL_H * t.K0;
+    t.w1t = base; base += RSL_H * RSL_H;
+    t.w1n = base; base += RSL_H * RSL_H;
+    t.b0 = base; base += RSL_H; t.b1 = base; base += RSL_H;
+    t.wh = base; base += RSL_H * 8; t.bh = base; base += 8;
+    t.dout = base;
+    return t;
+}
+// weights of one net into operand tiles: W0^T [64][K0] and W1^T [64][64] (B operands of F1 / F2), W1 [64][64] (B operand of B2)
+__device__ inline void tc_stage_net(const TcTile& t, const float* __restrict__ p, int D, int w0, int b0, int w1, int b1, int wh, int bh, int out) {
+    for (int i = threadIdx.x; i < t.K0 * RSL_H; i += blockDim.x) { int k = i / RSL_H, n = i % RSL_H; t.w0t[tile_off(n, k, t.K0)] = k < D ? p[w0 + k * RSL_H + n] : 0.f; }
+    for (int i = threadIdx.x; i < RSL_H * RSL_H; i += blockDim.x) {
+        int k = i / RSL_H, n = i % RSL_H; float w = p[w1 + i];
+        t.w1t[tile_off(n, k, RSL_H)] = w;          // [out j][in i]
+        t.w1n[tile_off(k, n, RSL_H)] = w;          // [in i][out j]
+    }
+    for (int i = threadIdx.x; i < RSL_H; i += blockDim.x) { t.b0[i] = p[b0 + i]; t.b1[i] = p[b1 + i]; }
+    for (int i = threadIdx.x; i < RSL_H * 8; i += blockDim.x) { int r = i >> 3, c = i & 7; t.wh[i] = c < out ? p[wh + r * out + c] : 0.f; }
+    if (threadIdx.x < 8) t.bh[threadIdx.x] = threadIdx.x < out ? p[bh + threadIdx.x] : 0.f;
+}
+__device__ inline void tc_stage_x(const TcTile& t, const float* __restrict__ X, size_t ldx, const int* __restrict__ idx, int row0, int n, int D) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < RSL_TILE; r += nw) {
+        int g = row0 + r;
+        const float* src = nullptr;
+        if (g < n) src = X + (size_t)(idx ? idx[g] : g) * ldx;
+        for (int k = lane; k < t.K0; k += 32) t.xs[tile_off(r, k, t.K0)] = (src && k < D) ? src[k] : 0.f;
+    }
+}
+struct TcCtx { uint32_t tmem; uint64_t* bar; uint32_t phase; };
+
+// D[tmem] = A[128 x K] * B^T with B given as [64 x K] tile (both K-major); called by all threads, issued by thread 0
+__device__ __forceinline__ void tc_gemm(TcCtx& c, const float* A, const float* Bt, int K) {
+    rstc::fence_async_smem();
+    rstc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rstc::tc_fence_after();
+        const uint32_t sbo = (K / 4) * 128;
+        rstc::umma_tf32(c.tmem, rstc::smem_u32(A), 128, sbo, 256, rstc::smem_u32(Bt), 128, sbo, 256, rstc::make_idesc(128, 64, 0, 0), K / 8, c.bar);
+    }
+    rstc::mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    rstc::tc_fence_after();
+}
+// epilogue of F1 / F2: row r = threadIdx.x of the accumulator -> relu(acc + bias) into an operand tile [128][64]
+__device__ __forceinline__ void tc_relu_to_tile(const TcCtx& c, const float* bias, float* tile) {
+    const int r = threadIdx.x;
+    float o[32];
+#pragma unroll
+    for (int c0 = 0; c0 < RSL_H; c0 += 32) {
+        rstc::tmem_ld32(c.tmem, c0, o);
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+            float4 v = make_float4(fmaxf(o[q] + bias[c0 + q], 0.f), fmaxf(o[q + 1] + bias[c0 + q + 1], 0.f),
+                                   fmaxf(o[q + 2] + bias[c0 + q + 2], 0.f), fmaxf(o[q + 3] + bias[c0 + q + 3], 0.f));
+            *reinterpret_cast<float4*>(tile + tile_off(r, c0 + q, RSL_H)) = v;
+        }
+    }
+}
+// forward of the staged net: H1, H2 tiles filled; head outputs of this thread's row in out8
+__device__ __forceinline__ void tc_net_forward(TcCtx& c, const TcTile& t, float* out8) {
+    tc_gemm(c, t.xs, t.w0t, t.K0);
+    tc_relu_to_tile(c, t.b0, t.h1);
+    tc_gemm(c, t.h1, t.w1t, RSL_H);
+    tc_relu_to_tile(c, t.b1, t.h2);
+    const int r = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 8; q++) out8[q] = t.bh[q];
+    for (int k = 0; k < RSL_H; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(t.h2 + tile_off(r, k, RSL_H));      // own writes: no barrier needed
+        const float av[4] = { a.x, a.y, a.z, a.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int q = 0; q < 8; q++) out8[q] = fmaf(av[u], t.wh[(k + u) * 8 + q], out8[q]);
+    }
+}
+__device__ __forceinline__ void tc_begin(TcCtx& c, uint64_t* bar, uint32_t* slot) {
+    if (threadIdx.x == 0) rstc::mbar_init(bar, 1);
+    if (threadIdx.x < 32) rstc::tmem_alloc(slot, 64);
+    rstc::tc_fence_before();
+    __syncthreads();
+    rstc::tc_fence_after();
+    c.tmem = *slot; c.bar = bar; c.phase = 0;
+}
+__device__ __forceinline__ void tc_end(TcCtx& c) {
+    rstc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) rstc::tmem_dealloc(c.tmem, 64);
+}
+
+// ---- inference ----
+__global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(const float* __restrict__ params, int D, int A, const float* __restrict__ X, size_t ldx,
+                                                               int n, float* __restrict__ mean, float* __restrict__ value) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const Layout L = make_layout(D, A);
+    TcTile t = tc_carve(smem, D);
+    TcCtx c;
+    tc_begin(c, &bar, &slot);
+    const int row0 = blockIdx.x * RSL_TILE, g = row0 + threadIdx.x;
+    tc_stage_x(t, X, ldx, nullptr, row0, n, D);
+    float o[8];
+    if (mean) {
+        tc_stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
+        tc_net_forward(c, t, o);
+        if (g < n) for (int q = 0; q < A; q++) mean[(size_t)g * A + q] = o[q];
+        rstc::tc_fence_before();
+        __syncthreads();
+    }
+    if (value) {
+        tc_stage_net(t, params, D, L.vf_w0, L.vf_b0, L.vf_w1, L.vf_b1, L.vf_w, L.vf_b, 1);
+        tc_net_forward(c, t, o);
+        if (g < n) value[g] = o[0];
+    }
+    tc_end(c);
+}
+
+// ---- gradients on the FP32 pipe, operands in core-matrix tiles: out[M x 64] = in^T dz over the tile rows ----
+__device__ inline void tc_grad_weight(const float* __restrict__ in, int C, int M, const float* __restrict__ dz, float* __restrict__ out, int rows) {
+    const int i0 = (threadIdx.x >> 3) * 8, j0 = (threadIdx.x & 7) * 8;
+    if (i0 >= M) return;
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b] = 0.f;
+    for (int r = 0; r < rows; r++) {
+        const float4 a0 = *reinterpret_cast<const float4*>(in + tile_off(r, i0, C)), a1 = *reinterpret_cast<const float4*>(in + tile_off(r, i0 + 4, C));
+        const float4 b0 = *reinterpret_cast<const float4*>(dz + tile_off(r, j0, RSL_H)), b1 = *reinterpret_cast<const float4*>(dz + tile_off(r, j0 + 4, RSL_H));
+        const float av[8] = { a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w }, bv[8] = { b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w };
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 8; b++) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) if (i0 + a < M)
+#pragma unroll
+        for (int b = 0; b < 8; b++) out[(i0 + a) * RSL_H + j0 + b] = acc[a][b];
+}
+__device__ inline void tc_grad_bias(const float* __restrict__ dz, float* __restrict__ out, int rows) {
+    if (threadIdx.x < RSL_H) {
+        float s = 0.f;
+        for (int r = 0; r < rows; r++) s += dz[tile_off(r, threadIdx.x, RSL_H)];
+        out[threadIdx.x] = s;
+    }
+}
+// dZ1 = relu'(H1) * (dZ2 * W1^T): GEMM B2 on the tensor core, mask epilogue, written in place of H1
+__device__ __forceinline__ void tc_backprop_hidden(TcCtx& c, const TcTile& t) {
+    tc_gemm(c, t.h2, t.w1n, RSL_H);                     // A = dZ2 (in the h2 tile), B rows = input unit i, K = output unit j
+    const int r = threadIdx.x;
+    float o[32];
+#pragma unroll
+    for (int c0 = 0; c0 < RSL_H; c0 += 32) {
+        rstc::tmem_ld32(c.tmem, c0, o);
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+            float4* p = reinterpret_cast<float4*>(t.h1 + tile_off(r, c0 + q, RSL_H));
+            float4 h = *p;
+            *p = make_float4(h.x > 0.f ? o[q] : 0.f, h.y > 0.f ? o[q + 1] : 0.f, h.z > 0.f ? o[q + 2] : 0.f, h.w > 0.f ? o[q + 3] : 0.f);
+        }
+    }
+}
+
+// one block = 128 samples: same contract as k_ppo_tile (per-block partial gradients and stat partials)
+__global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const Layout L = make_layout(a.D, a.A);
+    const int D = a.D, A = a.A;
+    TcTile t = tc_carve(smem, D);
+    TcCtx c;
+    tc_begin(c, &bar, &slot);
+    const int row0 = blockIdx.x * RSL_TILE, r = threadIdx.x, g = row0 + r;
+    const int rows = min(RSL_TILE, a.n - row0);
+    const bool live = g < a.n;
+    const int s = live ? (a.idx ? a.idx[g] : g) : 0;
+    float* gp = a.gpart + (size_t)blockIdx.x * L.P;
+    for (int i = threadIdx.x; i < L.P; i += blockDim.x) gp[i] = 0.f;
+    tc_stage_x(t, a.obs, (size_t)D, a.idx, row0, a.n, D);
+    // ---------------- policy net ----------------
+    tc_stage_net(t, a.params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
+    float mu[8];
+    tc_net_forward(c, t, mu);
+    const double mean = a.adv_sums[0] / a.adv_count;
+    const double var = fmax(a.adv_sums[1] / a.adv_count - mean * mean, 0.0);
+    const float adv_mean = (float)mean, adv_std = (float)sqrt(var);
+    float st_pg = 0.f, st_kl = 0.f, st_clip = 0.f, st_vf = 0.f;
+    float dmu[8], dls[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { dmu[q] = 0.f; dls[q] = 0.f; }
+    if (live) {
+        float ls[8], z[8], nl = 0.f, lsum = 0.f;
+        for (int q = 0; q < A; q++) {
+            ls[q] = a.params[L.logstd + q];
+            z[q] = (a.actions[(size_t)s * A + q] - mu[q]) * expf(-ls[q]);
+            nl += z[q] * z[q]; lsum += ls[q];
+        }
+        nl = 0.5f * nl + 0.9189385332046727f * (float)A + lsum;
+        const float old = a.old_nlp[s];
+        float ratio = expf(old - nl);
+        const bool isnan_ = ratio != ratio;
+        if (isnan_) ratio = 2.f;
+        const float adv = (a.returns[s] - a.values[s] - adv_mean) / (adv_std + 1e-8f);
+        const float w = a.weights ? a.weights[s] : 1.f;
+        const float rc = fminf(fmaxf(ratio, 1.f - a.cliprange), 1.f + a.cliprange);
+        const float pg1 = -adv * ratio, pg2 = -adv * rc;
+        st_pg = w * fmaxf(pg1, pg2);
+        st_kl = nl - old;
+        st_clip = fabsf(ratio - 1.f) > a.cliprange ? 1.f : 0.f;
+        if (a.log_ratio) a.log_ratio[g] = old - nl;
+        float gnl = 0.f;
+        if (!isnan_) {
+            const bool inside = (ratio >= 1.f - a.cliprange) && (ratio <= 1.f + a.cliprange);
+            if (pg1 >= pg2) gnl = adv * ratio; else if (inside) gnl = adv * ratio;
+        }
+        gnl *= w * a.inv_n;
+        for (int q = 0; q < A; q++) { dmu[q] = gnl * (-z[q] * expf(-ls[q])); dls[q] = gnl * (1.f - z[q] * z[q]); }
+    }
+    for (int q = 0; q < 8; q++) t.dout[r * 9 + q] = dmu[q];
+    t.dout[r * 9 + 8] = 0.f;
+    __syncthreads();
+    for (int o = threadIdx.x; o < RSL_H * A; o += blockDim.x) {
+        const int k = o / A, q = o - k * A;
+        float acc = 0.f;
+        for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, k, RSL_H)], t.dout[u * 9 + q], acc);
+        gp[L.pi_w + o] = acc;
+    }
+    if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * 9 + threadIdx.x]; gp[L.pi_b + threadIdx.x] = acc; }
+    __syncthreads();
+    for (int q = 0; q < 8; q++) t.dout[r * 9 + q] = dls[q];
+    __syncthreads();
+    if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * 9 + threadIdx.x]; gp[L.logstd + threadIdx.x] = acc; }
+    // dZ2 = relu'(H2) * (dmu Wp^T), in place of H2 (own row)
+    for (int k = 0; k < RSL_H; k++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc = fmaf(dmu[q], t.wh[k * 8 + q], acc);
+        float* p = t.h2 + tile_off(r, k, RSL_H);
+        *p = *p > 0.f ? acc : 0.f;
+    }
+    __syncthreads();
+    tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.pi_w1, rows);
+    tc_grad_bias(t.h2, gp + L.pi_b1, rows);
+    tc_backprop_hidden(c, t);                                              // dZ1 in place of H1 (tensor core)
+    __syncthreads();
+    tc_grad_weight(t.xs, t.K0, D, t.h1, gp + L.pi_w0, rows);
+    tc_grad_bias(t.h1, gp + L.pi_b0, rows);
+    rstc::tc_fence_before();
+    __syncthreads();
+    // ---------------- value net ----------------
+    tc_stage_net(t, a.params, D, L.vf_w0, L.vf_b0, L.vf_w1, L.vf_b1, L.vf_w, L.vf_b, 1);
+    float vo[8];
+    tc_net_forward(c, t, vo);
+    float dv = 0.f;
+    if (live) {
+        const float err = vo[0] - a.returns[s];
+        st_vf = 0.5f * err * err;
+        dv = a.vf_coef * err * a.inv_n;
+    }
+    t.dout[r * 9] = dv;
+    __syncthreads();
+    if (threadIdx.x < RSL_H) { float acc = 0.f; for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, threadIdx.x, RSL_H)], t.dout[u * 9], acc); gp[L.vf_w + threadIdx.x] = acc; }
+    if (threadIdx.x == 64) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * 9]; gp[L.vf_b] = acc; }
+    __syncthreads();
+    for (int k = 0; k < RSL_H; k++) { float* p = t.h2 + tile_off(r, k, RSL_H); *p = *p > 0.f ? dv * t.wh[k * 8] : 0.f; }
+    __syncthreads();
+    tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.vf_w1, rows);
+    tc_grad_bias(t.h2, gp + L.vf_b1, rows);
+    tc_backprop_hidden(c, t);
+    __syncthreads();
+    tc_grad_weight(t.xs, t.K0, D, t.h1, gp + L.vf_w0, rows);
+    tc_grad_bias(t.h1, gp + L.vf_b0, rows);
+    // ---------------- stat partials ----------------
+    float v4[4] = { st_pg, st_vf, st_kl, st_clip };
+    __syncthreads();
+    for (int k = 0; k < 4; k++) {
+        float x = v4[k];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0) t.dout[k * 4 + (threadIdx.x >> 5)] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) a.spart[(size_t)blockIdx.x * 8 + threadIdx.x] = t.dout[threadIdx.x * 4] + t.dout[threadIdx.x * 4 + 1] + t.dout[threadIdx.x * 4 + 2] + t.dout[threadIdx.x * 4 + 3];
+    tc_end(c);
+}
+
+}  // namespace rsl

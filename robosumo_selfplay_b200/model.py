@@ -19,7 +19,7 @@ class PPOModel:
     loss_names = ['policy_loss', 'value_loss', 'policy_entropy', 'approxkl', 'clipfrac']     # model.py:140
 
     def __init__(self, *, ob_dim, ac_dim, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, trainable=True, model_scope="",
-                 device=0, max_minibatch=1 << 20, comm=None, policy=None, ob_space=None, ac_space=None, **_ignored):
+                 device=0, max_minibatch=1 << 20, comm=None, policy=None, ob_space=None, ac_space=None, precision='tf32', **_ignored):
         import torch
         self.torch = torch
         self.D, self.A = ob_dim, ac_dim
@@ -32,7 +32,8 @@ class PPOModel:
         self._L = _lib.lib()
         assert self._L.rs_param_count(ob_dim, ac_dim) == self.P
         self.params = torch.as_tensor(init_params(ob_dim, ac_dim), device=self.device)       # consumes np.random like ortho_init
-        self.act_model = PolicyWithValue(self.params, ob_dim, ac_dim, seed=abs(hash(model_scope)) % 9973)
+        self.precision = precision
+        self.act_model = PolicyWithValue(self.params, ob_dim, ac_dim, seed=abs(hash(model_scope)) % 9973, precision=precision)
         self.train_model = types.SimpleNamespace(X=types.SimpleNamespace(dtype=types.SimpleNamespace(name='float32')))
         self.step = self.act_model.step
         self.value = self.act_model.value
@@ -85,7 +86,8 @@ class PPOModel:
         entropy = (self.act_model.logstd().double() + 0.5 * np.log(2.0 * np.pi * np.e)).sum()      # before the update (model.py:70)
         _lib.check(L.rs_ppo_grad(self._p(self.params), self.D, self.A, self._p(obs), self._p(actions), self._p(returns), self._p(values),
                                  self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(self.adv_sums), float(cliprange),
-                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio), st))
+                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio),
+                                 1 if self.precision == 'tf32' else 0, st))
         if self.comm is not None:
             self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums]: one latency-bound NCCL all-reduce
         self.t += 1

@@ -63,7 +63,7 @@ def logstd_offset(D, A):
 class PolicyWithValue:
     """step / value / action_probability over a flat parameter tensor (torch, CUDA, float32 [P])."""
 
-    def __init__(self, params, ob_dim, ac_dim, seed=0):
+    def __init__(self, params, ob_dim, ac_dim, seed=0, precision='tf32'):
         import torch
         self.torch = torch
         self.params = params
@@ -74,6 +74,7 @@ class PolicyWithValue:
         self._seed = seed
         self.initial_state = None
         self._ls0 = logstd_offset(ob_dim, ac_dim)
+        self.precision = precision                  # 'tf32': tcgen05 tensor cores; 'fp32': FP32 pipe (numerics reference)
 
     # ---- device primitives --------------------------------------------------------------
     def _stream(self):
@@ -98,7 +99,8 @@ class PolicyWithValue:
         value = t.empty((n,), dtype=t.float32, device=self.device) if want_value else None
         _lib.check(self._L.rs_mlp_forward(ctypes.c_void_p(self.params.data_ptr()), self.D, self.A, ctypes.c_void_p(obs.data_ptr()),
                                           obs.stride(0), n, ctypes.c_void_p(mean.data_ptr()) if want_mean else None,
-                                          ctypes.c_void_p(value.data_ptr()) if want_value else None, self._stream()))
+                                          ctypes.c_void_p(value.data_ptr()) if want_value else None,
+                                          1 if self.precision == 'tf32' else 0, self._stream()))
         return mean, value
 
     def neglogp_of(self, actions, mean):

@@ -10,13 +10,15 @@ GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 D, A = 121, 8
 
 
-def test_mlp_forward_and_neglogp_match_oracle():
-    """PolicyWithValue heads: |mean|,|value| err <= 2e-5 abs on O(1) outputs; neglogp rel 1e-5; ragged n, strided rows."""
+@pytest.mark.parametrize('precision,atol,rtol', [('fp32', 2e-5, 2e-5), ('tf32', 6e-3, 2e-3)])
+def test_mlp_forward_and_neglogp_match_oracle(precision, atol, rtol):
+    """PolicyWithValue heads, ragged n, strided rows.  FP32 pipe: |mean|,|value| err <= 2e-5 abs on O(1) outputs, neglogp rel
+    2e-5.  tcgen05 path (tf32 inputs, fp32 accumulate): 6e-3 abs / 2e-3 rel."""
     import torch
     from oracle import ppo_oracle as po
     from robosumo_selfplay_b200.model import PPOModel
     np.random.seed(3)
-    m = PPOModel(ob_dim=D, ac_dim=A)
+    m = PPOModel(ob_dim=D, ac_dim=A, precision=precision)
     flat = m.get_flat()
     flat += 0.05 * np.random.randn(flat.size).astype(np.float32)           # non-zero biases / logstd
     m.set_flat(flat)
@@ -25,16 +27,16 @@ def test_mlp_forward_and_neglogp_match_oracle():
         x = torch.as_tensor(obs2, device='cuda')[:, 1, :]                  # strided rows
         mean, val = m.act_model.forward(x)
         rm, rv, ls = po.forward(flat, obs2[:, 1, :], D, A)
-        np.testing.assert_allclose(mean.cpu().numpy(), rm, atol=2e-5)
-        np.testing.assert_allclose(val.cpu().numpy(), rv, atol=2e-5)
+        np.testing.assert_allclose(mean.cpu().numpy(), rm, atol=atol)
+        np.testing.assert_allclose(val.cpu().numpy(), rv, atol=atol)
         act = np.random.randn(n, A).astype(np.float32)
         nlp = m.act_model.action_probability(x, given_action=torch.as_tensor(act, device='cuda'))
-        np.testing.assert_allclose(nlp.cpu().numpy(), po.neglogp(act, rm, ls), rtol=2e-5)
+        np.testing.assert_allclose(nlp.cpu().numpy(), po.neglogp(act, rm, ls), rtol=rtol)
     a, v, s, nl = m.step(obs2[:, 0, :])                                     # numpy in -> numpy out
     assert a.shape == (300, A) and v.shape == (300,) and s is None and nl.shape == (300,)
     rm, rv, ls = po.forward(flat, obs2[:, 0, :], D, A)
-    np.testing.assert_allclose(nl, po.neglogp(a, rm, ls), rtol=2e-5)
-    np.testing.assert_allclose(m.value(obs2[:, 0, :]), rv, atol=2e-5)
+    np.testing.assert_allclose(nl, po.neglogp(a, rm, ls), rtol=rtol)
+    np.testing.assert_allclose(m.value(obs2[:, 0, :]), rv, atol=atol)
 
 
 @pytest.mark.parametrize('case', ['a', 'b', 'c'])
@@ -65,15 +67,19 @@ def test_vtrace_matches_reference_runner_golden(case):
     assert np.array_equal(sf01(dev('in_dones', torch.uint8)).cpu().numpy().astype(bool), g['dones'])
 
 
-@pytest.mark.parametrize('n,use_idx', [(128, False), (1000, True), (77, True)])
-def test_ppo_minibatch_step_matches_oracle(n, use_idx):
-    """PPOModel.train: 5 stats rel 1e-4 (abs 1e-6), gradient rel 2e-4 of its max, parameters after 3 Adam steps atol 2e-6."""
+@pytest.mark.parametrize('n,use_idx,precision', [(128, False, 'fp32'), (1000, True, 'fp32'), (77, True, 'fp32'), (1000, True, 'tf32'), (128, False, 'tf32')])
+def test_ppo_minibatch_step_matches_oracle(n, use_idx, precision):
+    """PPOModel.train.  FP32 pipe: 5 stats rel 1e-4 (abs 1e-6), gradient rel 2e-4 of its max, parameters after each Adam step
+    atol 2e-6.  tcgen05 path (tf32): stats rel 5e-3 + abs 2e-3 (neglogp ~ 11 carries ~1e-3 relative tf32 noise), gradient 1e-2 of its max, log-ratio 5e-3, parameters atol 2e-4
+    (Adam normalises the step to ~lr, so a sign-level gradient error moves a parameter by up to 2*lr = 2e-3 only where the
+    gradient is ~0; measured error is reported by the assertion)."""
+    tight = precision == 'fp32' 
     import torch
     from oracle import ppo_oracle as po
     from robosumo_selfplay_b200.model import PPOModel
     rng = np.random.RandomState(n)
     np.random.seed(n)
-    m = PPOModel(ob_dim=D, ac_dim=A, ent_coef=0.01)
+    m = PPOModel(ob_dim=D, ac_dim=A, ent_coef=0.01, precision=precision)
     flat = m.get_flat() + 0.02 * rng.randn(m.P).astype(np.float32)
     m.set_flat(flat)
     N = 1500
@@ -94,11 +100,16 @@ def test_ppo_minibatch_step_matches_oracle(n, use_idx):
         of, om_, ov, ostats, olr, ograd, ognorm = po.ppo_train_step(of, om_, ov, step, D, A, obs[idx], ret[idx], act[idx], val[idx], old[idx], w[idx],
                                                                      1e-3, 0.2, ent_coef=0.01)
         for a_, b_ in zip(got, ostats):
-            assert abs(a_ - b_) <= 1e-4 * abs(b_) + 1e-6, (step, got, ostats)
-        np.testing.assert_allclose(log_ratio.cpu().numpy(), olr, atol=2e-5)
-        assert abs(g_gpu - ograd).max() <= 2e-4 * abs(ograd).max(), step
-        assert abs(float(m.gnorm.item()) - ognorm) <= 1e-4 * ognorm
-        np.testing.assert_allclose(m.get_flat(), of, atol=2e-6)
+            assert abs(a_ - b_) <= (1e-4 * abs(b_) + 1e-6 if tight else 5e-3 * abs(b_) + 2e-3), (step, got, ostats)
+        np.testing.assert_allclose(log_ratio.cpu().numpy(), olr, atol=2e-5 if tight else 5e-3)
+        # tf32: a sample whose ratio sits on the clip boundary can change side under tf32 noise in neglogp -> discrete gradient change,
+        # visible on the 128-sample minibatch (1/128 of the gradient mass per sample)
+        assert abs(g_gpu - ograd).max() <= (2e-4 if tight else (1e-2 if n >= 1000 else 5e-2)) * abs(ograd).max(), (step, abs(g_gpu - ograd).max() / abs(ograd).max())
+        assert abs(float(m.gnorm.item()) - ognorm) <= (1e-4 if tight else 2e-2) * ognorm
+        if tight:
+            np.testing.assert_allclose(m.get_flat(), of, atol=2e-6)
+        else:
+            assert np.mean(abs(m.get_flat() - of)) < 2e-5 and abs(m.get_flat() - of).max() < 2.1e-3
         # keep the oracle on the fp32 trajectory so that errors do not compound through Adam's 1/sqrt(v)
         of = m.get_flat().astype(np.float64)
         om_ = m.m.cpu().numpy().astype(np.float64); ov = m.v.cpu().numpy().astype(np.float64)
@@ -108,7 +119,7 @@ def test_reference_train_signature_and_checkpoint_roundtrip(tmp_path):
     import joblib
     from robosumo_selfplay_b200.model import PPOModel
     np.random.seed(0)
-    m = PPOModel(ob_dim=D, ac_dim=A)
+    m = PPOModel(ob_dim=D, ac_dim=A)            # default precision: tcgen05 / tf32
     rng = np.random.RandomState(1)
     n = 256
     out = m.train(1e-3, 0.2, rng.randn(n, D), rng.randn(n), None, rng.randn(n, A), rng.randn(n), 8 + rng.randn(n), rng.randn(n), np.ones(n))
