@@ -439,10 +439,10 @@ int rs_param_count(int obs_dim, int act_dim) { return rsl::make_layout(obs_dim, 
 
 int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long ld, int n, float* mean, float* value,
                    int precision, void* stream) {
-    if (!params || !obs || n <= 0 || act_dim > 8 || (!mean && !value)) return fail(RS_ERR_ARG, "rs_mlp_forward: bad argument%s", "");
+    if (!params || !obs || n <= 0 || act_dim > RSL_HW || (!mean && !value)) return fail(RS_ERR_ARG, "rs_mlp_forward: bad argument%s", "");
+    if (precision == 1 && rsl::tc_tile_bytes(obs_dim) > 227 * 1024) precision = 0;     // wide observations: FP32-pipe kernel
     if (precision == 1) {
         size_t sm = rsl::tc_tile_bytes(obs_dim);
-        if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for the tensor-core tile%s", "");
         static std::atomic<size_t> cur(0);
         if (sm > cur.load()) { CUDA_OK(cudaFuncSetAttribute(rsl::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cur.store(sm); }
         rsl::k_mlp_forward_tc<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
@@ -510,10 +510,11 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
                 const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
                 const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
                 float* log_ratio, int precision, void* stream) {
-    if (!params || !obs || !grad_stats || !workspace || act_dim > 8 || n < 0 || global_n <= 0) return fail(RS_ERR_ARG, "rs_ppo_grad: bad argument%s", "");
+    if (!params || !obs || !grad_stats || !workspace || act_dim > RSL_HW || n < 0 || global_n <= 0) return fail(RS_ERR_ARG, "rs_ppo_grad: bad argument%s", "");
     const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { CUDA_OK(cudaMemsetAsync(grad_stats, 0, sizeof(float) * (L.P + 4), st)); return RS_OK; }
+    if (precision == 1 && rsl::tc_tile_bytes(obs_dim) > 227 * 1024) precision = 0;     // wide observations: FP32-pipe kernel
     size_t sm = precision == 1 ? rsl::tc_tile_bytes(obs_dim) : rsl::tile_bytes(obs_dim, act_dim);
     if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_ppo_grad: obs_dim too large for one tile%s", "");
     if (precision == 1) {

@@ -23,6 +23,8 @@ namespace rsl {
 #define RSL_H 64           // hidden width (defaults.py:24 num_hidden=64)
 #define RSL_TILE 128       // samples per block
 #define RSL_HP 65          // padded row stride of hidden tiles (conflict-free column access)
+#define RSL_HW 16          // head width the kernels pad to (action dim <= 16: ant 8, bug 12, spider 16; value head uses column 0)
+#define RSL_DS (RSL_HW + 1)
 
 struct Layout {
     int D, A, P;
@@ -43,33 +45,37 @@ __host__ __device__ inline Layout make_layout(int D, int A) {
 //   h1  [128][65], h2 [128][65]
 //   w0  [D][64], w1 [64][64], wh [64][OUTp], biases
 struct Tile {
-    float *xs, *h1, *h2, *w0, *b0, *w1, *b1, *wh, *bh, *dout;
+    float *xs, *h1, *h2, *w0, *b0, *w1, *b1, *wh, *bh, *dout;      // w0 may point to global memory (stage_w0)
     int Dp;
 };
 __host__ __device__ inline int row_stride(int D) { int p = (D + 3) & ~3; if ((p & 31) == 0) p += 4; return p | 1; }
+// first-layer weights are staged in shared memory when they fit next to the input tile; for the wide observations of the
+// six- and eight-legged bodies (D = 165 / 209) they are read through L1 instead (every thread reads the same address)
+__host__ __device__ inline bool stage_w0(int D) { return D <= 136; }
 __host__ __device__ inline size_t tile_bytes(int D, int A) {
-    return sizeof(float) * ((size_t)RSL_TILE * row_stride(D) + 2 * RSL_TILE * RSL_HP + (size_t)D * RSL_H + RSL_H + RSL_H * RSL_H + RSL_H
-                            + RSL_H * 8 + 8 + RSL_TILE * 9);
+    return sizeof(float) * ((size_t)RSL_TILE * row_stride(D) + 2 * RSL_TILE * RSL_HP + (stage_w0(D) ? (size_t)D * RSL_H : 0) + RSL_H + RSL_H * RSL_H + RSL_H
+                            + RSL_H * RSL_HW + RSL_HW + RSL_TILE * RSL_DS);
 }
 __device__ inline Tile carve(float* base, int D) {
     Tile t; t.Dp = row_stride(D);
     t.xs = base; base += RSL_TILE * t.Dp;
     t.h1 = base; base += RSL_TILE * RSL_HP;
     t.h2 = base; base += RSL_TILE * RSL_HP;
-    t.w0 = base; base += D * RSL_H; t.b0 = base; base += RSL_H;
+    t.w0 = base; base += stage_w0(D) ? D * RSL_H : 0; t.b0 = base; base += RSL_H;
     t.w1 = base; base += RSL_H * RSL_H; t.b1 = base; base += RSL_H;
-    t.wh = base; base += RSL_H * 8; t.bh = base; base += 8;
+    t.wh = base; base += RSL_H * RSL_HW; t.bh = base; base += RSL_HW;
     t.dout = base;
     return t;
 }
 
 // stage one net (trunk + head with `out` columns, out <= 8) into shared memory
-__device__ inline void stage_net(const Tile& t, const float* __restrict__ p, int D, int w0, int b0, int w1, int b1, int wh, int bh, int out) {
-    for (int i = threadIdx.x; i < D * RSL_H; i += blockDim.x) t.w0[i] = p[w0 + i];
+__device__ inline void stage_net(Tile& t, const float* __restrict__ p, int D, int w0, int b0, int w1, int b1, int wh, int bh, int out) {
+    if (stage_w0(D)) { for (int i = threadIdx.x; i < D * RSL_H; i += blockDim.x) t.w0[i] = p[w0 + i]; }
+    else t.w0 = const_cast<float*>(p + w0);
     for (int i = threadIdx.x; i < RSL_H * RSL_H; i += blockDim.x) t.w1[i] = p[w1 + i];
     for (int i = threadIdx.x; i < RSL_H; i += blockDim.x) { t.b0[i] = p[b0 + i]; t.b1[i] = p[b1 + i]; }
-    for (int i = threadIdx.x; i < RSL_H * 8; i += blockDim.x) { int r = i >> 3, c = i & 7; t.wh[i] = c < out ? p[wh + r * out + c] : 0.f; }
-    if (threadIdx.x < 8) t.bh[threadIdx.x] = threadIdx.x < out ? p[bh + threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < RSL_H * RSL_HW; i += blockDim.x) { int r = i / RSL_HW, c = i % RSL_HW; t.wh[i] = c < out ? p[wh + r * out + c] : 0.f; }
+    if (threadIdx.x < RSL_HW) t.bh[threadIdx.x] = threadIdx.x < out ? p[bh + threadIdx.x] : 0.f;
 }
 // stage input rows; idx == nullptr -> rows row0..row0+127 of X (row stride ldx); rows >= n are zero
 __device__ inline void stage_x(const Tile& t, const float* __restrict__ X, size_t ldx, const int* __restrict__ idx, int row0, int n, int D) {
@@ -100,16 +106,16 @@ __device__ __forceinline__ void dense_relu_row(const float* __restrict__ in, int
     for (int j = 0; j < RSL_H; j++) out_row[j] = fmaxf(acc[j], 0.f);
 }
 // forward of the staged net for this thread's row; head outputs (8 padded) returned in out8
-__device__ __forceinline__ void net_forward_row(const Tile& t, int D, float* out8) {
+__device__ __forceinline__ void net_forward_row(const Tile& t, int D, float* outh) {
     const int r = threadIdx.x;
     dense_relu_row(t.xs + r * t.Dp, D, t.w0, t.b0, t.h1 + r * RSL_HP);
     dense_relu_row(t.h1 + r * RSL_HP, RSL_H, t.w1, t.b1, t.h2 + r * RSL_HP);
 #pragma unroll
-    for (int c = 0; c < 8; c++) out8[c] = t.bh[c];
+    for (int c = 0; c < RSL_HW; c++) outh[c] = t.bh[c];
     for (int k = 0; k < RSL_H; k++) {
         const float a = t.h2[r * RSL_HP + k];
 #pragma unroll
-        for (int c = 0; c < 8; c++) out8[c] = fmaf(a, t.wh[k * 8 + c], out8[c]);
+        for (int c = 0; c < RSL_HW; c++) outh[c] = fmaf(a, t.wh[k * RSL_HW + c], outh[c]);
     }
 }
 
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(RSL_TILE) k_mlp_forward(const float* __restric
     Tile t = carve(smem, D);
     const int row0 = blockIdx.x * RSL_TILE, g = row0 + threadIdx.x;
     stage_x(t, X, ldx, nullptr, row0, n, D);
-    float o[8];
+    float o[RSL_HW];
     if (mean) {
         stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
         __syncthreads();
@@ -331,17 +337,17 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile(PPOArgs a) {
     // ---------------- policy net ----------------
     stage_net(t, a.params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
     __syncthreads();
-    float mu[8];
+    float mu[RSL_HW];
     net_forward_row(t, D, mu);
     const double mean = a.adv_sums[0] / a.adv_count;
     const double var = fmax(a.adv_sums[1] / a.adv_count - mean * mean, 0.0);
     const float adv_mean = (float)mean, adv_std = (float)sqrt(var);
     float st_pg = 0.f, st_kl = 0.f, st_clip = 0.f, st_vf = 0.f;
-    float dmu[8], dls[8];
+    float dmu[RSL_HW], dls[RSL_HW];
 #pragma unroll
-    for (int c = 0; c < 8; c++) { dmu[c] = 0.f; dls[c] = 0.f; }
+    for (int c = 0; c < RSL_HW; c++) { dmu[c] = 0.f; dls[c] = 0.f; }
     if (live) {
-        float ls[8], z[8], nl = 0.f, lsum = 0.f;
+        float ls[RSL_HW], z[RSL_HW], nl = 0.f, lsum = 0.f;
         for (int c = 0; c < A; c++) {
             ls[c] = a.params[L.logstd + c];
             z[c] = (a.actions[(size_t)s * A + c] - mu[c]) * expf(-ls[c]);
@@ -373,27 +379,27 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile(PPOArgs a) {
         }
     }
     // head grads: dWp[64][A] = h2^T dmu ; dbp ; dlogstd (column sums via the dout tile)
-    for (int c = 0; c < 8; c++) t.dout[r * 9 + c] = dmu[c];
-    t.dout[r * 9 + 8] = 0.f;
+    for (int c = 0; c < RSL_HW; c++) t.dout[r * RSL_DS + c] = dmu[c];
+    
     __syncthreads();
     for (int o = threadIdx.x; o < RSL_H * A; o += blockDim.x) {
         const int k = o / A, c = o - k * A;
         float acc = 0.f;
-        for (int q = 0; q < rows; q++) acc = fmaf(t.h2[q * RSL_HP + k], t.dout[q * 9 + c], acc);
+        for (int q = 0; q < rows; q++) acc = fmaf(t.h2[q * RSL_HP + k], t.dout[q * RSL_DS + c], acc);
         gp[L.pi_w + o] = acc;
     }
-    if (threadIdx.x < A) { float acc = 0.f; for (int q = 0; q < rows; q++) acc += t.dout[q * 9 + threadIdx.x]; gp[L.pi_b + threadIdx.x] = acc; }
+    if (threadIdx.x < A) { float acc = 0.f; for (int q = 0; q < rows; q++) acc += t.dout[q * RSL_DS + threadIdx.x]; gp[L.pi_b + threadIdx.x] = acc; }
     __syncthreads();
-    for (int c = 0; c < 8; c++) t.dout[r * 9 + c] = dls[c];
+    for (int c = 0; c < RSL_HW; c++) t.dout[r * RSL_DS + c] = dls[c];
     __syncthreads();
-    if (threadIdx.x < A) { float acc = 0.f; for (int q = 0; q < rows; q++) acc += t.dout[q * 9 + threadIdx.x]; gp[L.logstd + threadIdx.x] = acc; }
+    if (threadIdx.x < A) { float acc = 0.f; for (int q = 0; q < rows; q++) acc += t.dout[q * RSL_DS + threadIdx.x]; gp[L.logstd + threadIdx.x] = acc; }
     // dz2 = relu'(h2) * (dmu Wp^T), in place of h2
     {
         float* h2r = t.h2 + r * RSL_HP;
         for (int k = 0; k < RSL_H; k++) {
             float acc = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; c++) acc = fmaf(dmu[c], t.wh[k * 8 + c], acc);
+            for (int c = 0; c < RSL_HW; c++) acc = fmaf(dmu[c], t.wh[k * RSL_HW + c], acc);
             h2r[k] = h2r[k] > 0.f ? acc : 0.f;
         }
     }
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile(PPOArgs a) {
     // ---------------- value net ----------------
     stage_net(t, a.params, D, L.vf_w0, L.vf_b0, L.vf_w1, L.vf_b1, L.vf_w, L.vf_b, 1);
     __syncthreads();
-    float vo[8];
+    float vo[RSL_HW];
     net_forward_row(t, D, vo);
     float dv = 0.f;
     if (live) {
@@ -417,14 +423,14 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile(PPOArgs a) {
         st_vf = 0.5f * err * err;
         dv = a.vf_coef * err * a.inv_n;                                      // d (vf_coef * .5 mean(err^2)) / dv
     }
-    t.dout[r * 9] = dv;
+    t.dout[r * RSL_DS] = dv;
     __syncthreads();
-    if (threadIdx.x < RSL_H) { float acc = 0.f; for (int q = 0; q < rows; q++) acc = fmaf(t.h2[q * RSL_HP + threadIdx.x], t.dout[q * 9], acc); gp[L.vf_w + threadIdx.x] = acc; }
-    if (threadIdx.x == 64) { float acc = 0.f; for (int q = 0; q < rows; q++) acc += t.dout[q * 9]; gp[L.vf_b] = acc; }
+    if (threadIdx.x < RSL_H) { float acc = 0.f; for (int q = 0; q < rows; q++) acc = fmaf(t.h2[q * RSL_HP + threadIdx.x], t.dout[q * RSL_DS], acc); gp[L.vf_w + threadIdx.x] = acc; }
+    if (threadIdx.x == 64) { float acc = 0.f; for (int q = 0; q < rows; q++) acc += t.dout[q * RSL_DS]; gp[L.vf_b] = acc; }
     __syncthreads();
     {
         float* h2r = t.h2 + r * RSL_HP;
-        for (int k = 0; k < RSL_H; k++) h2r[k] = h2r[k] > 0.f ? dv * t.wh[k * 8] : 0.f;
+        for (int k = 0; k < RSL_H; k++) h2r[k] = h2r[k] > 0.f ? dv * t.wh[k * RSL_HW] : 0.f;
     }
     __syncthreads();
     grad_weight_tile(t.h1, RSL_HP, RSL_H, t.h2, gp + L.vf_w1, rows);

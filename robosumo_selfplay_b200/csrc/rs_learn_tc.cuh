@@ -24,7 +24,7 @@ struct TcTile {
 __host__ __device__ inline int tc_k0(int D) { return (D + 7) & ~7; }
 __host__ __device__ inline size_t tc_tile_bytes(int D) {
     const int K0 = tc_k0(D);
-    return sizeof(float) * ((size_t)RSL_TILE * K0 + 2 * RSL_TILE * RSL_H + (size_t)RSL_H * K0 + 2 * RSL_H * RSL_H + 2 * RSL_H + RSL_H * 8 + 8 + RSL_TILE * 9) + 1024;
+    return sizeof(float) * ((size_t)RSL_TILE * K0 + 2 * RSL_TILE * RSL_H + (size_t)RSL_H * K0 + 2 * RSL_H * RSL_H + 2 * RSL_H + RSL_H * RSL_HW + RSL_HW + RSL_TILE * RSL_DS) + 1024;
 }
 __device__ inline TcTile tc_carve(float* base, int D) {
     TcTile t; t.K0 = tc_k0(D);
@@ -35,7 +35,7 @@ __device__ inline TcTile tc_carve(float* base, int D) {
     t.w1t = base; base += RSL_H * RSL_H;
     t.w1n = base; base += RSL_H * RSL_H;
     t.b0 = base; base += RSL_H; t.b1 = base; base += RSL_H;
-    t.wh = base; base += RSL_H * 8; t.bh = base; base += 8;
+    t.wh = base; base += RSL_H * RSL_HW; t.bh = base; base += RSL_HW;
     t.dout = base;
     return t;
 }
@@ -48,8 +48,8 @@ __device__ inline void tc_stage_net(const TcTile& t, const float* __restrict__ p
         t.w1n[tile_off(k, n, RSL_H)] = w;          // [in i][out j]
     }
     for (int i = threadIdx.x; i < RSL_H; i += blockDim.x) { t.b0[i] = p[b0 + i]; t.b1[i] = p[b1 + i]; }
-    for (int i = threadIdx.x; i < RSL_H * 8; i += blockDim.x) { int r = i >> 3, c = i & 7; t.wh[i] = c < out ? p[wh + r * out + c] : 0.f; }
-    if (threadIdx.x < 8) t.bh[threadIdx.x] = threadIdx.x < out ? p[bh + threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < RSL_H * RSL_HW; i += blockDim.x) { int r = i / RSL_HW, c = i % RSL_HW; t.wh[i] = c < out ? p[wh + r * out + c] : 0.f; }
+    if (threadIdx.x < RSL_HW) t.bh[threadIdx.x] = threadIdx.x < out ? p[bh + threadIdx.x] : 0.f;
 }
 __device__ inline void tc_stage_x(const TcTile& t, const float* __restrict__ X, size_t ldx, const int* __restrict__ idx, int row0, int n, int D) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -92,21 +92,21 @@ __device__ __forceinline__ void tc_relu_to_tile(const TcCtx& c, const float* bia
     }
 }
 // forward of the staged net: H1, H2 tiles filled; head outputs of this thread's row in out8
-__device__ __forceinline__ void tc_net_forward(TcCtx& c, const TcTile& t, float* out8) {
+__device__ __forceinline__ void tc_net_forward(TcCtx& c, const TcTile& t, float* outh) {
     tc_gemm(c, t.xs, t.w0t, t.K0);
     tc_relu_to_tile(c, t.b0, t.h1);
     tc_gemm(c, t.h1, t.w1t, RSL_H);
     tc_relu_to_tile(c, t.b1, t.h2);
     const int r = threadIdx.x;
 #pragma unroll
-    for (int q = 0; q < 8; q++) out8[q] = t.bh[q];
+    for (int q = 0; q < RSL_HW; q++) outh[q] = t.bh[q];
     for (int k = 0; k < RSL_H; k += 4) {
         const float4 a = *reinterpret_cast<const float4*>(t.h2 + tile_off(r, k, RSL_H));      // own writes: no barrier needed
         const float av[4] = { a.x, a.y, a.z, a.w };
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
-            for (int q = 0; q < 8; q++) out8[q] = fmaf(av[u], t.wh[(k + u) * 8 + q], out8[q]);
+            for (int q = 0; q < RSL_HW; q++) outh[q] = fmaf(av[u], t.wh[(k + u) * RSL_HW + q], outh[q]);
     }
 }
 __device__ __forceinline__ void tc_begin(TcCtx& c, uint64_t* bar, uint32_t* slot) {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(const float* __rest
     tc_begin(c, &bar, &slot);
     const int row0 = blockIdx.x * RSL_TILE, g = row0 + threadIdx.x;
     tc_stage_x(t, X, ldx, nullptr, row0, n, D);
-    float o[8];
+    float o[RSL_HW];
     if (mean) {
         tc_stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
         tc_net_forward(c, t, o);
@@ -217,17 +217,17 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     tc_stage_x(t, a.obs, (size_t)D, a.idx, row0, a.n, D);
     // ---------------- policy net ----------------
     tc_stage_net(t, a.params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
-    float mu[8];
+    float mu[RSL_HW];
     tc_net_forward(c, t, mu);
     const double mean = a.adv_sums[0] / a.adv_count;
     const double var = fmax(a.adv_sums[1] / a.adv_count - mean * mean, 0.0);
     const float adv_mean = (float)mean, adv_std = (float)sqrt(var);
     float st_pg = 0.f, st_kl = 0.f, st_clip = 0.f, st_vf = 0.f;
-    float dmu[8], dls[8];
+    float dmu[RSL_HW], dls[RSL_HW];
 #pragma unroll
-    for (int q = 0; q < 8; q++) { dmu[q] = 0.f; dls[q] = 0.f; }
+    for (int q = 0; q < RSL_HW; q++) { dmu[q] = 0.f; dls[q] = 0.f; }
     if (live) {
-        float ls[8], z[8], nl = 0.f, lsum = 0.f;
+        float ls[RSL_HW], z[RSL_HW], nl = 0.f, lsum = 0.f;
         for (int q = 0; q < A; q++) {
             ls[q] = a.params[L.logstd + q];
             z[q] = (a.actions[(size_t)s * A + q] - mu[q]) * expf(-ls[q]);
@@ -254,25 +254,25 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
         gnl *= w * a.inv_n;
         for (int q = 0; q < A; q++) { dmu[q] = gnl * (-z[q] * expf(-ls[q])); dls[q] = gnl * (1.f - z[q] * z[q]); }
     }
-    for (int q = 0; q < 8; q++) t.dout[r * 9 + q] = dmu[q];
-    t.dout[r * 9 + 8] = 0.f;
+    for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = dmu[q];
+    
     __syncthreads();
     for (int o = threadIdx.x; o < RSL_H * A; o += blockDim.x) {
         const int k = o / A, q = o - k * A;
         float acc = 0.f;
-        for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, k, RSL_H)], t.dout[u * 9 + q], acc);
+        for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, k, RSL_H)], t.dout[u * RSL_DS + q], acc);
         gp[L.pi_w + o] = acc;
     }
-    if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * 9 + threadIdx.x]; gp[L.pi_b + threadIdx.x] = acc; }
+    if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * RSL_DS + threadIdx.x]; gp[L.pi_b + threadIdx.x] = acc; }
     __syncthreads();
-    for (int q = 0; q < 8; q++) t.dout[r * 9 + q] = dls[q];
+    for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = dls[q];
     __syncthreads();
-    if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * 9 + threadIdx.x]; gp[L.logstd + threadIdx.x] = acc; }
+    if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * RSL_DS + threadIdx.x]; gp[L.logstd + threadIdx.x] = acc; }
     // dZ2 = relu'(H2) * (dmu Wp^T), in place of H2 (own row)
     for (int k = 0; k < RSL_H; k++) {
         float acc = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc = fmaf(dmu[q], t.wh[k * 8 + q], acc);
+        for (int q = 0; q < RSL_HW; q++) acc = fmaf(dmu[q], t.wh[k * RSL_HW + q], acc);
         float* p = t.h2 + tile_off(r, k, RSL_H);
         *p = *p > 0.f ? acc : 0.f;
     }
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     __syncthreads();
     // ---------------- value net ----------------
     tc_stage_net(t, a.params, D, L.vf_w0, L.vf_b0, L.vf_w1, L.vf_b1, L.vf_w, L.vf_b, 1);
-    float vo[8];
+    float vo[RSL_HW];
     tc_net_forward(c, t, vo);
     float dv = 0.f;
     if (live) {
@@ -295,12 +295,12 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
         st_vf = 0.5f * err * err;
         dv = a.vf_coef * err * a.inv_n;
     }
-    t.dout[r * 9] = dv;
+    t.dout[r * RSL_DS] = dv;
     __syncthreads();
-    if (threadIdx.x < RSL_H) { float acc = 0.f; for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, threadIdx.x, RSL_H)], t.dout[u * 9], acc); gp[L.vf_w + threadIdx.x] = acc; }
-    if (threadIdx.x == 64) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * 9]; gp[L.vf_b] = acc; }
+    if (threadIdx.x < RSL_H) { float acc = 0.f; for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, threadIdx.x, RSL_H)], t.dout[u * RSL_DS], acc); gp[L.vf_w + threadIdx.x] = acc; }
+    if (threadIdx.x == 64) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * RSL_DS]; gp[L.vf_b] = acc; }
     __syncthreads();
-    for (int k = 0; k < RSL_H; k++) { float* p = t.h2 + tile_off(r, k, RSL_H); *p = *p > 0.f ? dv * t.wh[k * 8] : 0.f; }
+    for (int k = 0; k < RSL_H; k++) { float* p = t.h2 + tile_off(r, k, RSL_H); *p = *p > 0.f ? dv * t.wh[k * RSL_HW] : 0.f; }
     __syncthreads();
     tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.vf_w1, rows);
     tc_grad_bias(t.h2, gp + L.vf_b1, rows);

@@ -178,3 +178,34 @@ def test_runner_and_learn_end_to_end_small():
         assert np.array_equal(a_, b_)                                      # bit-exact permutation
     assert [h['opponent'] for h in model.history] == opp
     assert np.isfinite(model.get_flat()).all()
+
+
+@pytest.mark.parametrize('Dw,Aw', [(165, 12), (209, 16)])
+def test_wide_observation_morphologies_train_step(Dw, Aw):
+    """Bug (D=165, A=12) and Spider (D=209, A=16) learner shapes: first-layer weights are read through L1 instead of being
+    staged and the tensor-core tile does not fit, so the FP32-pipe kernels run; forward and one train step against the oracle."""
+    import torch
+    from oracle import ppo_oracle as po
+    from robosumo_selfplay_b200.model import PPOModel
+    rng = np.random.RandomState(Dw)
+    np.random.seed(Dw)
+    m = PPOModel(ob_dim=Dw, ac_dim=Aw)
+    flat = m.get_flat() + 0.02 * rng.randn(m.P).astype(np.float32)
+    m.set_flat(flat)
+    N = 300
+    obs = rng.randn(N, Dw).astype(np.float32); act = rng.randn(N, Aw).astype(np.float32) * 0.5
+    ret = rng.randn(N).astype(np.float32) * 2; val = rng.randn(N).astype(np.float32)
+    rm, rv, ls = po.forward(flat, obs, Dw, Aw)
+    mean, value = m.act_model.forward(torch.as_tensor(obs, device='cuda'))
+    np.testing.assert_allclose(mean.cpu().numpy(), rm, atol=3e-5); np.testing.assert_allclose(value.cpu().numpy(), rv, atol=3e-5)
+    old = (po.neglogp(act, rm, ls) + 0.3 * rng.randn(N)).astype(np.float32)
+    w = np.ones(N, np.float32)
+    d = lambda x: torch.as_tensor(x, device='cuda')
+    stats, _ = m.train_indexed(1e-3, 0.2, d(obs), d(ret), d(act), d(val), d(old), d(w), None)
+    got = m.stats_to_list(stats)
+    g_gpu = m.grad_stats[:m.P].cpu().numpy().astype(np.float64)
+    of, om_, ov, ostats, olr, ograd, ognorm = po.ppo_train_step(flat.astype(np.float64), np.zeros(m.P), np.zeros(m.P), 1, Dw, Aw, obs, ret, act, val, old, w, 1e-3, 0.2)
+    for a_, b_ in zip(got, ostats):
+        assert abs(a_ - b_) <= 1e-4 * abs(b_) + 1e-6, (got, ostats)
+    assert abs(g_gpu - ograd).max() <= 2e-4 * abs(ograd).max()
+    np.testing.assert_allclose(m.get_flat(), of, atol=2e-6)
