@@ -37,6 +37,7 @@
 #define RS_SYNC() __syncwarp()
 #define RS_ATOMIC_ADDF(p, v) atomicAdd((p), (v))
 #define RS_ATOMIC_INC(p) atomicAdd((p), 1)
+#define RS_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define RS_LANE0 ((threadIdx.x & 31) == 0)
 #define RS_RCP(x) __frcp_rn(x)
 #define RS_RSQRT(x) (1.0f / sqrtf(x))      /* fast intrinsics (rsqrtf, __sincosf, __fdividef) were measured: no speed-up, parity loss */
@@ -48,6 +49,7 @@
 #define RS_SYNC()
 #define RS_ATOMIC_ADDF(p, v) (*(p) += (v))
 #define RS_ATOMIC_INC(p) ((*(p))++)
+#define RS_ATOMIC_OR(p, v) (*(p) |= (v))
 #define RS_LANE0 (true)
 #define RS_RCP(x) (1.0f / (x))
 #define RS_RSQRT(x) (1.0f / sqrtf(x))
@@ -139,6 +141,7 @@ struct Slab {
     float lsgn[NU], lD[NU], laref[NU], ljar[NU];
     float scr[64];                  // per-contact direction Jacobians: idx(16 as float) + 3 x 16
     int ncon, status, niter, same, coupled;
+    int lmask, pmask, pvalid;                 // limit rows: active set in use / predicted from the previous evaluation / prediction valid
     int tot_iter, tot_coupled, tot_ncon;      // diagnostics accumulated over one env step
     RS_HD float* legI(int g) { return &caref[0][0] + 10 * g; }
     RS_HD int bA(int k) const { return (cbody[k] & 255) - 1; }
@@ -631,6 +634,8 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
     const float tc = fmaxf(0.02f, 2.f * c.h);
     const float Kc = 1.f / (RS_DMAX * RS_DMAX * tc * tc), Bc = 2.f / (RS_DMAX * tc);
     // limits first: sign and D, then J v through rows_of
+    if (RS_LANE0) { s.pmask = 0; s.pvalid = 0; }
+    RS_SYNC();
     RS_LANE_LOOP(j, S::NU) {
         int g = j >> 1, a = c.agent_of_leg(g), l = g - c.leg0(a), isank = j & 1;
         const rs_agent_model& m = c.am[a];
@@ -638,6 +643,9 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         float lo = isank ? m.lo_ank[l] : m.lo_hip[l], hi = isank ? m.hi_ank[l] : m.hi_hip[l];
         float sgn = 0.f, pos = 0.f;
         if (qv - lo < 0.f) { sgn = 1.f; pos = qv - lo; } else if (hi - qv < 0.f) { sgn = -1.f; pos = hi - qv; }
+        // the row's state at the previous evaluation's solution predicts its state now far better than the sign of the
+        // residual at the warm start does (aref moves by B * dvel between RK stages, more than |jar| of a loaded row)
+        if (sgn != 0.f && s.lsgn[j] == sgn) { RS_ATOMIC_OR(&s.pvalid, 1 << j); if (s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.pmask, 1 << j); }
         s.lsgn[j] = sgn;
         float imp = impedance(pos);
         float diag = isank ? m.iwd_ank[l] : m.iwd_hip[l];
@@ -695,8 +703,8 @@ RS_HD void jt_forces(Ctx<LA, LB>& c) {
         V3 Ta = ld3(s.wr[c.bank(g)]), Fa = ld3(s.wr[c.bank(g)] + 3);
         V3 Fh = ld3(s.wr[c.bhip(g)] + 3) + Fa;
         V3 Th = ld3(s.wr[c.bhip(g)]) + Ta + cross(pa - ph, Fa);
-        float fl_h = s.ljar[2 * g] < 0.f ? -s.lD[2 * g] * s.ljar[2 * g] : 0.f;
-        float fl_a = s.ljar[2 * g + 1] < 0.f ? -s.lD[2 * g + 1] * s.ljar[2 * g + 1] : 0.f;
+        float fl_h = ((s.lmask >> (2 * g)) & 1) ? -s.lD[2 * g] * s.ljar[2 * g] : 0.f;
+        float fl_a = ((s.lmask >> (2 * g + 1)) & 1) ? -s.lD[2 * g + 1] * s.ljar[2 * g + 1] : 0.f;
         s.jtf[dh] = dot(ld3(s.axh[g]), Th) + s.lsgn[2 * g] * fl_h;
         s.jtf[dh + 1] = dot(ld3(s.axa[g]), Ta) + s.lsgn[2 * g + 1] * fl_a;
         st3(s.legF[g], Th); st3(s.legF[g] + 3, Fh);     // about the hip origin
@@ -768,7 +776,7 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
         } else {
             const int l = (k - 6) >> 1, isank = (k - 6) & 1, g = c.leg0(a) + l, dh = va + 6 + 2 * l, j = 2 * g + isank;
             for (int kk = 0; kk < 6; kk++) H[s.hidx(i, va + kk)] = s.Mc[g][2 * kk + isank];
-            const float lim = s.ljar[j] < 0.f ? s.lD[j] : 0.f;
+            const float lim = ((s.lmask >> j) & 1) ? s.lD[j] : 0.f;
             H[s.hidx(i, dh)] = isank ? s.Ml[g][1] : s.Ml[g][0] + lim;
             H[s.hidx(i, dh + 1)] = isank ? s.Ml[g][2] + lim : s.Ml[g][1];
         }
@@ -969,6 +977,9 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         if (first) {
             RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] -= s.caref[k][r]; }
             RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
+            if (RS_LANE0) s.lmask = s.pmask & s.pvalid;
+            RS_SYNC();
+            RS_LANE_LOOP(j, S::NU) { if (s.ljar[j] < 0.f && !((s.pvalid >> j) & 1)) RS_ATOMIC_OR(&s.lmask, 1 << j); }
             RS_SYNC();
             continue;
         }
@@ -979,12 +990,16 @@ RS_HD void solve(Ctx<LA, LB>& c) {
             for (int r = 0; r < 4; r++) if ((s.cjar[k][r] < 0.f) != (s.cjar[k][r] + s.cjd[k][r] < 0.f)) s.same = 0;
         }
         RS_LANE_LOOP(j, S::NU) {
-            if (s.lsgn[j] != 0.f && ((s.ljar[j] < 0.f) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
+            if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
         }
+        // was the set used for this iteration the sign set at the current point?  (not when it came from the prediction)
+        if (RS_LANE0) s.pvalid = 0;
         RS_SYNC();
-        const int same = s.same;
+        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] < 0.f))) s.pvalid = 1; }
+        RS_SYNC();
+        const int same = s.same, predicted = s.pvalid;
         float alpha = 1.f;
-        if (!same) {
+        if (!same && !predicted) {
             // exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton inside a bracket
             const float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
             float lo = 0.f, hi = 0.f, d1, d2;
@@ -1003,6 +1018,9 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; }
         RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] += alpha * s.cjd[k][r]; }
         RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
+        if (RS_LANE0) s.lmask = 0;
+        RS_SYNC();
+        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.lmask, 1 << j); }     // sign set at the new point
         RS_SYNC();
         it++;
         if (same) conv = true;
