@@ -100,7 +100,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     envs = 16 * cores
-    per_step_s = 2.0
+    per_step_s = 0.5          # bounded sample per step so that the default K / W finish within ~2 minutes
     vals = []
     for i in range(args.warmup + args.steps):
         rate, n, el = cpu_port_rate(per_step_s, envs, cores)
@@ -182,9 +182,9 @@ def measure_learner(args, E, local, rank, world, dev):
     roll_s, upd_s = float(tt[0]), float(tt[1])
     flops = 114.6e3 * N * nep
     return {'rollout': {'value': E * world * T / roll_s, 'unit': 'env-steps/s', 'T': T, 'launches_per_step': roll_launches / T,
-                        'note': 'Runner.run: 4 MLP launches + 1 sampling launch + 1 physics launch per step, no host sync'},
+                        'note': 'Runner.run: 1 fused MLP launch (4 policy evaluations, tcgen05 tf32) + 1 sampling launch + 1 physics launch per step, no host sync'},
             'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
-                           'higher_is_better': False, 'dtype': 'f32', 'achieved_tflops': flops / upd_s / 1e12,
+                           'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_s / 1e12,
                            'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,
                            'note': 'wall clock incl. host-side NumPy shuffles (bit-exact schedule) and the gradient all-reduce when N > 1'}}
 
@@ -291,7 +291,7 @@ def main():
     peak, peak_src = read_peaks()
     achieved = ALGO_BYTES_PER_PAIR_STEP * E / (ms_per_step / 1e3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'k_step_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'k_step_traffic.json')          # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')

@@ -21,6 +21,10 @@ class rs_config(ctypes.Structure):
                 ('seed', ctypes.c_uint64), ('device', c_int), ('reserved', c_int)]
 
 
+class rs_mlp_job(ctypes.Structure):
+    _fields_ = [('params', c_void_p), ('obs', c_void_p), ('obs_row_stride', ctypes.c_longlong), ('mean', c_void_p), ('value', c_void_p)]
+
+
 # every symbol include/rs_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'rs_agent_model_size': (c_int, []),
@@ -39,6 +43,7 @@ SYMBOLS = {
     'rs_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'rs_param_count': (c_int, [c_int, c_int]),
     'rs_mlp_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'rs_mlp_forward_multi': (c_int, [ctypes.POINTER(rs_mlp_job), c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'rs_rollout_sample': (c_int, [c_int, c_int] + [c_void_p] * 6 + [ctypes.c_ulonglong, ctypes.c_uint, c_int] + [c_void_p] * 6),
     'rs_neglogp': (c_int, [c_int, c_int] + [c_void_p] * 5),
     'rs_vtrace': (c_int, [c_int, c_int, c_float, c_float, c_float, c_float] + [c_void_p] * 10),

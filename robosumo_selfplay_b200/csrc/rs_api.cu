@@ -26,6 +26,11 @@
 #define RS_EVAL_SYNC() __syncthreads()
 #elif RS_SYNC_MODE == 2
 #define RS_SUBSTEP_SYNC() __syncthreads()
+#elif RS_SYNC_MODE == 4
+#define RS_SOLVE_SYNC() __syncthreads()
+#elif RS_SYNC_MODE == 5
+#define RS_EVAL_SYNC() __syncthreads()
+#define RS_SOLVE_SYNC() __syncthreads()
 #elif RS_SYNC_MODE == 3
 #define RS_EVAL_SYNC() rs_group_sync()
 __device__ __forceinline__ void rs_group_sync() {
@@ -437,24 +442,43 @@ static int ensure_smem(const void* fn, size_t bytes) {
 
 int rs_param_count(int obs_dim, int act_dim) { return rsl::make_layout(obs_dim, act_dim).P; }
 
-int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long ld, int n, float* mean, float* value,
-                   int precision, void* stream) {
-    if (!params || !obs || n <= 0 || act_dim > RSL_HW || (!mean && !value)) return fail(RS_ERR_ARG, "rs_mlp_forward: bad argument%s", "");
+static int mlp_forward_jobs(const rsl::MlpJobs& J, int njobs, int obs_dim, int act_dim, int n, int precision, void* stream) {
     if (precision == 1 && rsl::tc_tile_bytes(obs_dim) > 227 * 1024) precision = 0;     // wide observations: FP32-pipe kernel
+    dim3 grid((n + RSL_TILE - 1) / RSL_TILE, njobs);
     if (precision == 1) {
         size_t sm = rsl::tc_tile_bytes(obs_dim);
         static std::atomic<size_t> cur(0);
         if (sm > cur.load()) { CUDA_OK(cudaFuncSetAttribute(rsl::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cur.store(sm); }
-        rsl::k_mlp_forward_tc<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
+        rsl::k_mlp_forward_tc<<<grid, RSL_TILE, sm, (cudaStream_t)stream>>>(J, obs_dim, act_dim, n);
     } else {
         size_t sm = rsl::tile_bytes(obs_dim, act_dim);
         if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for one tile%s", "");
         int rc = ensure_smem((const void*)rsl::k_mlp_forward, sm); if (rc) return rc;
-        rsl::k_mlp_forward<<<(n + RSL_TILE - 1) / RSL_TILE, RSL_TILE, sm, (cudaStream_t)stream>>>(params, obs_dim, act_dim, obs, (size_t)ld, n, mean, value);
+        rsl::k_mlp_forward<<<grid, RSL_TILE, sm, (cudaStream_t)stream>>>(J, obs_dim, act_dim, n);
     }
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
+}
+
+int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long ld, int n, float* mean, float* value,
+                   int precision, void* stream) {
+    if (!params || !obs || n <= 0 || act_dim > RSL_HW || (!mean && !value)) return fail(RS_ERR_ARG, "rs_mlp_forward: bad argument%s", "");
+    rsl::MlpJobs J;
+    memset(&J, 0, sizeof(J));
+    J.params[0] = params; J.X[0] = obs; J.ldx[0] = (size_t)ld; J.mean[0] = mean; J.value[0] = value;
+    return mlp_forward_jobs(J, 1, obs_dim, act_dim, n, precision, stream);
+}
+
+int rs_mlp_forward_multi(const rs_mlp_job* jobs, int njobs, int obs_dim, int act_dim, int n, int precision, void* stream) {
+    if (!jobs || njobs < 1 || njobs > 4 || n <= 0 || act_dim > RSL_HW) return fail(RS_ERR_ARG, "rs_mlp_forward_multi: bad argument%s", "");
+    rsl::MlpJobs J;
+    memset(&J, 0, sizeof(J));
+    for (int i = 0; i < njobs; i++) {
+        if (!jobs[i].params || !jobs[i].obs || (!jobs[i].mean && !jobs[i].value)) return fail(RS_ERR_ARG, "rs_mlp_forward_multi: bad job%s", "");
+        J.params[i] = jobs[i].params; J.X[i] = jobs[i].obs; J.ldx[i] = (size_t)jobs[i].obs_row_stride; J.mean[i] = jobs[i].mean; J.value[i] = jobs[i].value;
+    }
+    return mlp_forward_jobs(J, njobs, obs_dim, act_dim, n, precision, stream);
 }
 
 int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* logstd1, const float* mu00, const float* mu10,

@@ -1036,6 +1036,9 @@ RS_HD void solve(Ctx<LA, LB>& c) {
 #ifndef RS_SUBSTEP_SYNC
 #define RS_SUBSTEP_SYNC()
 #endif
+#ifndef RS_SOLVE_SYNC
+#define RS_SOLVE_SYNC()
+#endif
 template <int LA, int LB>
 RS_HD void forward(Ctx<LA, LB>& c) {
     RS_EVAL_SYNC();     // optional block-wide re-alignment of the warps (instruction-cache locality)
@@ -1047,6 +1050,7 @@ RS_HD void forward(Ctx<LA, LB>& c) {
     RS_PHASE_SYNC();
     make_constraints(c);
     RS_PHASE_SYNC();
+    RS_SOLVE_SYNC();
     solve(c);
 }
 

@@ -119,14 +119,22 @@ __device__ __forceinline__ void net_forward_row(const Tile& t, int D, float* out
     }
 }
 
-// ---- inference: mean [n, A] and/or value [n] ---------------------------------------------------
-__global__ void __launch_bounds__(RSL_TILE) k_mlp_forward(const float* __restrict__ params, int D, int A, const float* __restrict__ X, size_t ldx,
-                                                            int n, float* __restrict__ mean, float* __restrict__ value) {
+// ---- inference: mean [n, A] and/or value [n]; up to 4 independent jobs per launch (blockIdx.y), e.g. the four
+//      (policy, observation) combinations of one rollout step (runner.py:62-97) ----
+struct MlpJobs {
+    const float* params[4]; const float* X[4]; float* mean[4]; float* value[4];
+    size_t ldx[4];
+};
+__global__ void __launch_bounds__(RSL_TILE) k_mlp_forward(MlpJobs J, int D, int A, int n) {
     extern __shared__ __align__(16) float smem[];
     const Layout L = make_layout(D, A);
     Tile t = carve(smem, D);
+    const int job = blockIdx.y;
+    const float* __restrict__ params = J.params[job];
+    float* __restrict__ mean = J.mean[job];
+    float* __restrict__ value = J.value[job];
     const int row0 = blockIdx.x * RSL_TILE, g = row0 + threadIdx.x;
-    stage_x(t, X, ldx, nullptr, row0, n, D);
+    stage_x(t, J.X[job], J.ldx[job], nullptr, row0, n, D);
     float o[RSL_HW];
     if (mean) {
         stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);

@@ -123,9 +123,8 @@ __device__ __forceinline__ void tc_end(TcCtx& c) {
     if (threadIdx.x < 32) rstc::tmem_dealloc(c.tmem, 64);
 }
 
-// ---- inference ----
-__global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(const float* __restrict__ params, int D, int A, const float* __restrict__ X, size_t ldx,
-                                                               int n, float* __restrict__ mean, float* __restrict__ value) {
+// ---- inference (same job contract as k_mlp_forward) ----
+__global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(MlpJobs J, int D, int A, int n) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
@@ -133,8 +132,12 @@ __global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(const float* __rest
     TcTile t = tc_carve(smem, D);
     TcCtx c;
     tc_begin(c, &bar, &slot);
+    const int job = blockIdx.y;
+    const float* __restrict__ params = J.params[job];
+    float* __restrict__ mean = J.mean[job];
+    float* __restrict__ value = J.value[job];
     const int row0 = blockIdx.x * RSL_TILE, g = row0 + threadIdx.x;
-    tc_stage_x(t, X, ldx, nullptr, row0, n, D);
+    tc_stage_x(t, J.X[job], J.ldx[job], nullptr, row0, n, D);
     float o[RSL_HW];
     if (mean) {
         tc_stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);

@@ -79,12 +79,21 @@ class Runner:
         m0, m1 = self.models[0].act_model, self.models[1].act_model
         ls0, ls1 = m0.logstd().contiguous(), m1.logstd().contiguous()
         host_epinfos = []
+        mu00 = t.empty((E, A), **f32); mu10 = t.empty((E, A), **f32); mu11 = t.empty((E, A), **f32); mu01 = t.empty((E, A), **f32)
+        v00 = t.empty((E,), **f32); v01 = t.empty((E,), **f32)
+        jobs = (_lib.rs_mlp_job * 4)()
+        stride = self.obs.stride(0)
+        for k, (mm, mu, vv) in enumerate(((m0, mu00, v00), (m1, mu10, None), (m1, mu11, None), (m0, mu01, v01))):
+            jobs[k].params = mm.params.data_ptr(); jobs[k].obs_row_stride = stride
+            jobs[k].mean = mu.data_ptr(); jobs[k].value = vv.data_ptr() if vv is not None else None
+        prec = 1 if m0.precision == 'tf32' else 0
         for step in range(T):
             o0, o1 = self.obs[:, 0, :], self.obs[:, 1, :]
-            mu00, v00 = m0.forward(o0)                              # models[0].step(obs[:, 0])                    runner.py:67
-            mu10, _ = m1.forward(o0, want_value=False)              # models[1].action_probability(obs[:, 0], a0)  runner.py:85
-            mu11, _ = m1.forward(o1, want_value=False)              # models[1].step(obs[:, 1])                    runner.py:67
-            mu01, v01 = m0.forward(o1)                              # models[0].value / action_probability(obs[:, 1], a1)   runner.py:89-90
+            # the four policy evaluations of runner.py:67-90 in ONE launch (blockIdx.y = job):
+            #   models[0].step(obs[:,0]) | models[1].action_probability(obs[:,0], a0) | models[1].step(obs[:,1]) |
+            #   models[0].value + action_probability(obs[:,1], a1)
+            jobs[0].obs = jobs[1].obs = o0.data_ptr(); jobs[2].obs = jobs[3].obs = o1.data_ptr()
+            _lib.check(self._L.rs_mlp_forward_multi(jobs, 4, D, A, E, prec, self._stream()))
             mb_obs[0, step].copy_(o0); mb_obs[1, step].copy_(o1)
             mb_dones[:, step].copy_(self.dones.t())
             mb_values[0, step].copy_(v00); mb_values[1, step].copy_(v01)
