@@ -133,8 +133,8 @@ int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, in
  * a_lbo,a_sbo,a_step,b_lbo,b_sbo,b_step,nk} (bytes), host pointer */
 int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, void* stream);
 
-/* diagnostics of the last rs_step: int[E][3] = (Newton iterations, evaluations with an inter-agent contact,
- * contacts) summed over the 20 forward evaluations of the step (cf. mjData.solver_iter / ncon) */
+/* diagnostics of the last rs_step: int[E][4] = (Newton iterations, evaluations with an inter-agent contact, contacts) summed over
+ * the 20 forward evaluations of the step, and the largest iteration count of a single evaluation (cf. mjData.solver_iter / ncon) */
 int rs_get_diag(rs_env* h, int* diag, void* stream);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */

@@ -63,7 +63,7 @@ static int fail(int code, const char* fmt, const char* detail) {
 struct EnvDev {
     int E;
     float *qpos, *qvel, *warm, *ep_ret, *ep_dret;
-    int *ep_step, *status, *diag;      // diag[E][3]: Newton iterations, coupled evaluations, contacts summed over the last env step
+    int *ep_step, *status, *diag;      // diag[E][4]: Newton iterations, coupled evaluations, contacts summed over the last env step, max iterations of one evaluation
     unsigned int* ep_count;
     const rs_agent_model* am;
     EnvParams P;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void load_state(Ctx<LA, LB>& c, const EnvDev& d, int 
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NQ) { s.q[i] = d.qpos[(size_t)e * S::NQ + i]; }
     RS_LANE_LOOP(i, S::NV) { s.v[i] = d.qvel[(size_t)e * S::NV + i]; s.x[i] = d.warm[(size_t)e * S::NV + i]; }
-    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; }
+    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; s.max_iter = 0; }
     RS_SYNC();
 }
 template <int LA, int LB>
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     env_rewards(c, d.P, before, act, num_steps, d.h * d.P.frame_skip, &o);
     float er = d.ep_ret[e] + o.rew[0], edr = d.ep_dret[e] + o.info[0][6];
     if (!live) return;
-    if (lane == 0) { d.diag[3 * e] = s.tot_iter; d.diag[3 * e + 1] = s.tot_coupled; d.diag[3 * e + 2] = s.tot_ncon; }
+    if (lane == 0) { d.diag[4 * e] = s.tot_iter; d.diag[4 * e + 1] = s.tot_coupled; d.diag[4 * e + 2] = s.tot_ncon; d.diag[4 * e + 3] = s.max_iter; }
     if (lane == 0) {
         rew[2 * e] = o.rew[0]; rew[2 * e + 1] = o.rew[1];
         done[2 * e] = (uint8_t)o.done[0]; done[2 * e + 1] = (uint8_t)o.done[1];
@@ -301,7 +301,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     CUDA_OK(cudaMalloc(&d.warm, sizeof(float) * E * h->nv)); CUDA_OK(cudaMalloc(&d.ep_ret, sizeof(float) * E));
     CUDA_OK(cudaMalloc(&d.ep_dret, sizeof(float) * E)); CUDA_OK(cudaMalloc(&d.ep_step, sizeof(int) * E));
     CUDA_OK(cudaMalloc(&d.status, sizeof(int) * E)); CUDA_OK(cudaMalloc(&d.ep_count, sizeof(unsigned int) * E));
-    CUDA_OK(cudaMalloc(&d.diag, sizeof(int) * E * 3)); CUDA_OK(cudaMemset(d.diag, 0, sizeof(int) * E * 3));
+    CUDA_OK(cudaMalloc(&d.diag, sizeof(int) * E * 4)); CUDA_OK(cudaMemset(d.diag, 0, sizeof(int) * E * 4));
     CUDA_OK(cudaMemset(d.qpos, 0, sizeof(float) * E * h->nq)); CUDA_OK(cudaMemset(d.qvel, 0, sizeof(float) * E * h->nv));
     CUDA_OK(cudaMemset(d.warm, 0, sizeof(float) * E * h->nv)); CUDA_OK(cudaMemset(d.ep_ret, 0, sizeof(float) * E));
     CUDA_OK(cudaMemset(d.ep_dret, 0, sizeof(float) * E)); CUDA_OK(cudaMemset(d.ep_step, 0, sizeof(int) * E));
@@ -412,7 +412,7 @@ int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_
 
 int rs_get_diag(rs_env* h, int* diag, void* stream) {
     if (!h || !diag) return fail(RS_ERR_ARG, "rs_get_diag: bad argument%s", "");
-    CUDA_OK(cudaMemcpyAsync(diag, h->d.diag, sizeof(int) * h->d.E * 3, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CUDA_OK(cudaMemcpyAsync(diag, h->d.diag, sizeof(int) * h->d.E * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return RS_OK;
 }
 

@@ -142,7 +142,7 @@ struct Slab {
     float scr[64];                  // per-contact direction Jacobians: idx(16 as float) + 3 x 16
     int ncon, status, niter, same, coupled;
     int lmask, pmask, pvalid;                 // limit rows: active set in use / predicted from the previous evaluation / prediction valid
-    int tot_iter, tot_coupled, tot_ncon;      // diagnostics accumulated over one env step
+    int tot_iter, tot_coupled, tot_ncon, max_iter;      // diagnostics accumulated over one env step
     RS_HD float* legI(int g) { return &caref[0][0] + 10 * g; }
     RS_HD int bA(int k) const { return (cbody[k] & 255) - 1; }
     RS_HD int bB(int k) const { return (cbody[k] >> 8) - 1; }
@@ -1025,7 +1025,7 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         it++;
         if (same) conv = true;
     }
-    if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled; s.tot_ncon += s.ncon; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
+    if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled; s.tot_ncon += s.ncon; if (it > s.max_iter) s.max_iter = it; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
     RS_SYNC();
 }
 

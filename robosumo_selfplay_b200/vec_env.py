@@ -270,9 +270,9 @@ class B200SumoVecEnv(VecEnv):
         return qacc, ncon, nit
 
     def diagnostics(self):
-        """int32 [E, 3]: Newton iterations, coupled evaluations, contacts -- each summed over the last step's 20 evaluations."""
+        """int32 [E, 4]: Newton iterations, coupled evaluations, contacts (summed over the last step's 20 evaluations), max iterations."""
         t = self.torch
-        out = t.empty((self.num_envs, 3), dtype=t.int32, device=self.device)
+        out = t.empty((self.num_envs, 4), dtype=t.int32, device=self.device)
         _lib.check(self._L.rs_get_diag(self._h, ctypes.c_void_p(out.data_ptr()), self._stream()))
         return out
 
