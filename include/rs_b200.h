@@ -107,7 +107,8 @@ int rs_param_count(int obs_dim, int act_dim);
 int rs_mlp_forward(const float* params, int obs_dim, int act_dim, const float* obs, long long obs_row_stride, int n,
                    float* mean, float* value, int precision, void* stream);
 /* up to 4 independent (params, obs) evaluations in ONE launch: the four policy evaluations of a rollout step (runner.py:62-97) */
-typedef struct rs_mlp_job { const float* params; const float* obs; long long obs_row_stride; float* mean; float* value; } rs_mlp_job;
+typedef struct rs_mlp_job { const float* params; const float* obs; long long obs_row_stride; float* mean; float* value;
+                            int activation /* 0 relu (policies.py), 1 tanh (policy_zoo/policy.py:52,64) */; int reserved; } rs_mlp_job;
 int rs_mlp_forward_multi(const rs_mlp_job* jobs /* host array */, int njobs, int obs_dim, int act_dim, int n, int precision, void* stream);
 /* one rollout step of Runner.run (runner.py:62-100): sample a0 ~ pi0(o0), a1 ~ pi1(o1) and the four neglogps */
 int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* logstd1, const float* mu00, const float* mu10,

@@ -177,3 +177,31 @@ def minibatch_schedule(seed, D, A, nupdates, N, nminibatches, noptepochs, oppone
                 mbs.append(inds[start:start + nbt].copy())
         sched.append(mbs)
     return opp, sched
+
+
+def zoo_mlp_act(flat, obs, D, A):
+    """Deterministic action and vpred of policy_zoo's MLPPolicy (robosumo/robosumo/policy_zoo/policy.py:39-80, utils.py:8-30,70-82)
+    from its flat parameter vector, float64."""
+    flat = np.asarray(flat, dtype=np.float64).ravel()
+    o = [0]
+
+    def take(*shp):
+        n = int(np.prod(shp)) if shp else 1
+        v = flat[o[0]:o[0] + n]
+        o[0] += n
+        return v.reshape(shp) if shp else float(v[0])
+    rs, rss, rc = take(), take(), take()
+    os_, oss, oc = take(D), take(D), take()
+    vf = [take(D, H), take(H), take(H, H), take(H), take(H, 1), take(1)]
+    pi = [take(D, H), take(H), take(H, H), take(H), take(H, A), take(A)]
+    take(1, A)
+    assert o[0] == flat.size
+    mean = os_ / oc
+    std = np.sqrt(np.maximum(oss / oc - mean ** 2, 1e-2))
+    obz = np.clip((np.asarray(obs, dtype=np.float64) - mean) / std, -5.0, 5.0)
+    h = np.tanh(np.tanh(obz @ vf[0] + vf[1]) @ vf[2] + vf[3])
+    vz = (h @ vf[4] + vf[5])[:, 0]
+    rmean = rs / rc
+    rstd = np.sqrt(max(rss / rc - rmean ** 2, 1e-2))
+    g = np.tanh(np.tanh(obz @ pi[0] + pi[1]) @ pi[2] + pi[3])
+    return g @ pi[4] + pi[5], vz * rstd + rmean

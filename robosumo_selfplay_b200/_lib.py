@@ -22,7 +22,8 @@ class rs_config(ctypes.Structure):
 
 
 class rs_mlp_job(ctypes.Structure):
-    _fields_ = [('params', c_void_p), ('obs', c_void_p), ('obs_row_stride', ctypes.c_longlong), ('mean', c_void_p), ('value', c_void_p)]
+    _fields_ = [('params', c_void_p), ('obs', c_void_p), ('obs_row_stride', ctypes.c_longlong), ('mean', c_void_p), ('value', c_void_p),
+                ('activation', c_int), ('reserved', c_int)]
 
 
 # every symbol include/rs_b200.h declares: name -> (restype, argtypes)

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'rs_api.cu')
 OUT = os.path.join(HERE, 'librs_b200.so')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('rs_api.cu', 'rs_core.h', 'rs_env.h', 'rs_learn.cuh')] + \
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('rs_api.cu', 'rs_core.h', 'rs_env.h', 'rs_learn.cuh', 'rs_learn_tc.cuh', 'rs_tc.cuh')] + \
        [os.path.join(os.path.dirname(HERE), 'include', 'rs_b200.h')]
 
 
@@ -21,10 +21,15 @@ def nvcc():
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+    if not force and not os.environ.get('RS_DEV_ANT_ONLY') and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
         return OUT
     cmd = [nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC', '-o', OUT, SRC]
+    if os.environ.get('RS_DEV_ANT_ONLY'):      # developer build: Ant-vs-Ant only, written next to the variants; select it with RS_B200_LIB
+        cmd.insert(1, '-DRS_DEV_ANT_ONLY')
+        dev = os.path.join(os.path.dirname(HERE), 'build', 'variants', 'librs_dev.so')
+        os.makedirs(os.path.dirname(dev), exist_ok=True)
+        cmd[cmd.index(OUT)] = dev
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

@@ -254,16 +254,22 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_forward_debug(EnvDev d, const f
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// morphology pairs: legs per agent in {4 (ant), 6 (bug), 8 (spider)}, all nine combinations (robosumo/__init__.py:8-105)
+#ifdef RS_DEV_ANT_ONLY      /* developer builds: only Ant-vs-Ant (the full build takes ~85 s) */
+#define RS_FOR_PAIRS(X) X(4, 4)
+#else
+#define RS_FOR_PAIRS(X) X(4, 4) X(4, 6) X(4, 8) X(6, 4) X(6, 6) X(6, 8) X(8, 4) X(8, 6) X(8, 8)
+#endif
 template <typename F> static int dispatch(const rs_env* h, F f) {
-    if (h->LA == 4 && h->LB == 4) return f(std::integral_constant<int, 4>(), std::integral_constant<int, 4>());
-    if (h->LA == 6 && h->LB == 6) return f(std::integral_constant<int, 6>(), std::integral_constant<int, 6>());
-    if (h->LA == 8 && h->LB == 8) return f(std::integral_constant<int, 8>(), std::integral_constant<int, 8>());
+#define RS_CASE(A, B) if (h->LA == A && h->LB == B) return f(std::integral_constant<int, A>(), std::integral_constant<int, B>());
+    RS_FOR_PAIRS(RS_CASE)
+#undef RS_CASE
     return fail(RS_ERR_UNSUPPORTED, "unsupported morphology pair (%s)", "legs");
 }
 static size_t slab_bytes(int LA, int LB) {
-    if (LA == 4 && LB == 4) return sizeof(Slab<4, 4>);
-    if (LA == 6 && LB == 6) return sizeof(Slab<6, 6>);
-    if (LA == 8 && LB == 8) return sizeof(Slab<8, 8>);
+#define RS_CASE(A, B) if (LA == A && LB == B) return sizeof(Slab<A, B>);
+    RS_FOR_PAIRS(RS_CASE)
+#undef RS_CASE
     return 0;
 }
 
@@ -476,7 +482,8 @@ int rs_mlp_forward_multi(const rs_mlp_job* jobs, int njobs, int obs_dim, int act
     memset(&J, 0, sizeof(J));
     for (int i = 0; i < njobs; i++) {
         if (!jobs[i].params || !jobs[i].obs || (!jobs[i].mean && !jobs[i].value)) return fail(RS_ERR_ARG, "rs_mlp_forward_multi: bad job%s", "");
-        J.params[i] = jobs[i].params; J.X[i] = jobs[i].obs; J.ldx[i] = (size_t)jobs[i].obs_row_stride; J.mean[i] = jobs[i].mean; J.value[i] = jobs[i].value;
+        J.params[i] = jobs[i].params; J.X[i] = jobs[i].obs; J.ldx[i] = (size_t)jobs[i].obs_row_stride; J.mean[i] = jobs[i].mean; J.value[i] = jobs[i].value; J.act[i] = jobs[i].activation;
+        if (jobs[i].activation) precision = 0;      // tanh nets (policy_zoo opponents) run on the FP32-pipe kernel
     }
     return mlp_forward_jobs(J, njobs, obs_dim, act_dim, n, precision, stream);
 }

@@ -88,7 +88,7 @@ __device__ inline void stage_x(const Tile& t, const float* __restrict__ X, size_
     }
 }
 // one thread = one sample row: out[64] = relu(in[row][:K] * W[K][64] + b)
-__device__ __forceinline__ void dense_relu_row(const float* __restrict__ in, int K, const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ out_row) {
+__device__ __forceinline__ void dense_relu_row(const float* __restrict__ in, int K, const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ out_row, int act = 0) {
     float acc[RSL_H];
 #pragma unroll
     for (int j = 0; j < RSL_H; j++) acc[j] = b[j];
@@ -103,13 +103,13 @@ __device__ __forceinline__ void dense_relu_row(const float* __restrict__ in, int
         }
     }
 #pragma unroll
-    for (int j = 0; j < RSL_H; j++) out_row[j] = fmaxf(acc[j], 0.f);
+    for (int j = 0; j < RSL_H; j++) out_row[j] = act ? tanhf(acc[j]) : fmaxf(acc[j], 0.f);      // relu (models.py:93-101) | tanh (policy_zoo/policy.py:52,64)
 }
 // forward of the staged net for this thread's row; head outputs (8 padded) returned in out8
-__device__ __forceinline__ void net_forward_row(const Tile& t, int D, float* outh) {
+__device__ __forceinline__ void net_forward_row(const Tile& t, int D, float* outh, int act = 0) {
     const int r = threadIdx.x;
-    dense_relu_row(t.xs + r * t.Dp, D, t.w0, t.b0, t.h1 + r * RSL_HP);
-    dense_relu_row(t.h1 + r * RSL_HP, RSL_H, t.w1, t.b1, t.h2 + r * RSL_HP);
+    dense_relu_row(t.xs + r * t.Dp, D, t.w0, t.b0, t.h1 + r * RSL_HP, act);
+    dense_relu_row(t.h1 + r * RSL_HP, RSL_H, t.w1, t.b1, t.h2 + r * RSL_HP, act);
 #pragma unroll
     for (int c = 0; c < RSL_HW; c++) outh[c] = t.bh[c];
     for (int k = 0; k < RSL_H; k++) {
@@ -124,6 +124,7 @@ __device__ __forceinline__ void net_forward_row(const Tile& t, int D, float* out
 struct MlpJobs {
     const float* params[4]; const float* X[4]; float* mean[4]; float* value[4];
     size_t ldx[4];
+    int act[4];          // hidden activation: 0 relu, 1 tanh
 };
 __global__ void __launch_bounds__(RSL_TILE) k_mlp_forward(MlpJobs J, int D, int A, int n) {
     extern __shared__ __align__(16) float smem[];
@@ -139,14 +140,14 @@ __global__ void __launch_bounds__(RSL_TILE) k_mlp_forward(MlpJobs J, int D, int 
     if (mean) {
         stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
         __syncthreads();
-        net_forward_row(t, D, o);
+        net_forward_row(t, D, o, J.act[job]);
         if (g < n) for (int c = 0; c < A; c++) mean[(size_t)g * A + c] = o[c];
         __syncthreads();
     }
     if (value) {
         stage_net(t, params, D, L.vf_w0, L.vf_b0, L.vf_w1, L.vf_b1, L.vf_w, L.vf_b, 1);
         __syncthreads();
-        net_forward_row(t, D, o);
+        net_forward_row(t, D, o, J.act[job]);
         if (g < n) value[g] = o[0];
     }
 }

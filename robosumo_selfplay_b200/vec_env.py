@@ -139,8 +139,8 @@ class B200SumoVecEnv(VecEnv):
         self._L = L
         oa, ob = self.pair.obs_dims
         aa, ab = self.pair.act_dims
-        if oa != ob:
-            raise NotImplementedError("mixed-morphology pairs need ragged obs; not built yet")
+        self.mixed = (oa != ob)            # mixed morphologies: ragged obs / actions, returned per agent
+        self.obs_dims, self.act_dims = (oa, ob), (aa, ab)
         self.obs_dim, self.act_dim = oa, aa
         self.nq, self.nv, self.nu = self.pair.nq, self.pair.nv, self.pair.nu
         ospace = Tuple([Box(-np.inf, np.inf, (oa,)), Box(-np.inf, np.inf, (ob,))])
@@ -148,12 +148,12 @@ class B200SumoVecEnv(VecEnv):
         VecEnv.__init__(self, num_envs, ospace, aspace)
         E = num_envs
         dev = self.device
-        self.d_obs = torch.zeros((E, 2, oa), dtype=torch.float32, device=dev)
+        self.d_obs = torch.zeros((E, oa + ob) if self.mixed else (E, 2, oa), dtype=torch.float32, device=dev)
         self.d_rew = torch.zeros((E, 2), dtype=torch.float32, device=dev)
         self.d_done = torch.zeros((E, 2), dtype=torch.uint8, device=dev)
         self.d_info = torch.zeros((E, 2, 8), dtype=torch.float32, device=dev)
         self.d_epi = torch.zeros((E, 3), dtype=torch.float32, device=dev)
-        self.h_obs = np.zeros((E, 2, oa), dtype=np.float32)
+        self.h_obs = np.zeros((E, oa + ob) if self.mixed else (E, 2, oa), dtype=np.float32)
         self.h_rew = np.zeros((E, 2), dtype=np.float32)
         self.h_done = np.zeros((E, 2), dtype=np.uint8)
         self.h_info = np.zeros((E, 2, 8), dtype=np.float32)
@@ -182,9 +182,20 @@ class B200SumoVecEnv(VecEnv):
             m = self.torch.as_tensor(mask, dtype=self.torch.uint8, device=self.device).contiguous()
         _lib.check(self._L.rs_reset(self._h, ctypes.c_void_p(m.data_ptr()) if m is not None else None,
                                     ctypes.c_void_p(self.d_obs.data_ptr()), self._stream()))
-        if self.device_api:
-            return self.d_obs
-        return self.d_obs.cpu().numpy().astype(np.float64)
+        return self._obs_out(self.d_obs if self.device_api else self.d_obs.cpu().numpy().astype(np.float64))
+
+    def _obs_out(self, obs):
+        """Same-morphology pairs: [E, 2, D].  Mixed pairs: tuple (obs_a [E, Da], obs_b [E, Db])."""
+        if not self.mixed:
+            return obs
+        return obs[:, :self.obs_dims[0]], obs[:, self.obs_dims[0]:]
+
+    def _flat_actions(self, actions):
+        if isinstance(actions, (tuple, list)) and len(actions) == 2 and getattr(actions[0], 'ndim', 0) == 2:
+            if self.torch.is_tensor(actions[0]):
+                return self.torch.cat([actions[0], actions[1]], 1)
+            return np.concatenate([np.asarray(actions[0]), np.asarray(actions[1])], 1)
+        return actions.reshape(self.num_envs, self.nu)
 
     def step_async(self, actions):
         self._assert_not_closed()
@@ -196,20 +207,20 @@ class B200SumoVecEnv(VecEnv):
         actions = self._pending
         self.waiting = False
         if self.device_api:
-            a = actions.reshape(self.num_envs, self.nu)
+            a = self._flat_actions(actions)
             if a.dtype != self.torch.float32 or not a.is_contiguous():
                 a = a.to(self.torch.float32).contiguous()
             _lib.check(self._L.rs_step(self._h, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(self.d_obs.data_ptr()),
                                        ctypes.c_void_p(self.d_rew.data_ptr()), ctypes.c_void_p(self.d_done.data_ptr()),
                                        ctypes.c_void_p(self.d_info.data_ptr()), ctypes.c_void_p(self.d_epi.data_ptr()),
                                        1 if self.auto_reset else 0, self._stream()))
-            return self.d_obs, self.d_rew, self.d_done, (self.d_info, self.d_epi)
-        a = np.ascontiguousarray(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.nu))
+            return self._obs_out(self.d_obs), self.d_rew, self.d_done, (self.d_info, self.d_epi)
+        a = np.ascontiguousarray(np.asarray(self._flat_actions(actions), dtype=np.float32).reshape(self.num_envs, self.nu))
         self.torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self._L.rs_step_host(self._h, self._np(a), self._np(self.h_obs), self._np(self.h_rew),
                                         self._np(self.h_done), self._np(self.h_info), self._np(self.h_epi),
                                         1 if self.auto_reset else 0))
-        return (self.h_obs.astype(np.float64), self.h_rew.astype(np.float64), self.h_done.astype(bool),
+        return (self._obs_out(self.h_obs.astype(np.float64)), self.h_rew.astype(np.float64), self.h_done.astype(bool),
                 self._infos_as_dicts())
 
     def _infos_as_dicts(self):
@@ -244,7 +255,7 @@ class B200SumoVecEnv(VecEnv):
         _lib.check(self._L.rs_set_state(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()),
                                         ctypes.c_void_p(self.d_obs.data_ptr()), self._stream()))
         t.cuda.current_stream(self.device).synchronize()
-        return self.d_obs if self.device_api else self.d_obs.cpu().numpy().astype(np.float64)
+        return self._obs_out(self.d_obs if self.device_api else self.d_obs.cpu().numpy().astype(np.float64))
 
     def get_state(self):
         t = self.torch

@@ -48,6 +48,8 @@ int emu_forward(const rs_agent_model* am, float h, int max_newton, const float* 
     if (LA == 4 && LB == 4) return run_forward<4, 4>(am, h, max_newton, q, v, ctrl, qacc, Mout, tau, ncon, niter, con, qnorm);
     if (LA == 6 && LB == 6) return run_forward<6, 6>(am, h, max_newton, q, v, ctrl, qacc, Mout, tau, ncon, niter, con, qnorm);
     if (LA == 8 && LB == 8) return run_forward<8, 8>(am, h, max_newton, q, v, ctrl, qacc, Mout, tau, ncon, niter, con, qnorm);
+    if (LA == 4 && LB == 6) return run_forward<4, 6>(am, h, max_newton, q, v, ctrl, qacc, Mout, tau, ncon, niter, con, qnorm);
+    if (LA == 8 && LB == 4) return run_forward<8, 4>(am, h, max_newton, q, v, ctrl, qacc, Mout, tau, ncon, niter, con, qnorm);
     return -1;
 }
 int emu_step(const rs_agent_model* am, float h, int max_newton, float* q, float* v, float* warm, const float* ctrl, int nsub) {
@@ -55,6 +57,8 @@ int emu_step(const rs_agent_model* am, float h, int max_newton, float* q, float*
     if (LA == 4 && LB == 4) return run_step<4, 4>(am, h, max_newton, q, v, warm, ctrl, nsub);
     if (LA == 6 && LB == 6) return run_step<6, 6>(am, h, max_newton, q, v, warm, ctrl, nsub);
     if (LA == 8 && LB == 8) return run_step<8, 8>(am, h, max_newton, q, v, warm, ctrl, nsub);
+    if (LA == 4 && LB == 6) return run_step<4, 6>(am, h, max_newton, q, v, warm, ctrl, nsub);
+    if (LA == 8 && LB == 4) return run_step<8, 4>(am, h, max_newton, q, v, warm, ctrl, nsub);
     return -1;
 }
 int emu_slab_bytes(int LA, int LB) {

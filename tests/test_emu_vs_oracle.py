@@ -90,3 +90,21 @@ def test_trajectory_bug_spider_with_self_collisions(name, emu, oracle_models):
         assert st == 0
         assert abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3, t
     assert seen >= 2
+
+
+@pytest.mark.parametrize('na,nb', [('ant', 'bug'), ('spider', 'ant')])
+def test_trajectory_mixed_morphology_pairs(na, nb, emu):
+    """Mixed pairs of robosumo/__init__.py (different dof counts per agent -> unequal diagonal blocks in the solver)."""
+    from oracle.physics import OracleModel, load_model_json
+    om = OracleModel(load_model_json('%s_%s' % (na, nb))); ps = PairSpec(na, nb)
+    rng = np.random.RandomState(2)
+    q = om.qpos0.copy(); phi = rng.uniform(0, 2 * np.pi)
+    for a, o in ((0, 0), (1, ps.agents[0].nq)):
+        q[o] = 1.15 * np.cos(phi + a * np.pi); q[o + 1] = 1.15 * np.sin(phi + a * np.pi); q[o + 2] = 1.25
+    q += rng.uniform(-.1, .1, om.nq); v = 0.1 * rng.randn(om.nv); om.normalize_qpos(q); w = np.zeros(om.nv)
+    qf, vf, wf = q.astype(np.float32), v.astype(np.float32), np.zeros(om.nv, np.float32)
+    for t in range(12):
+        ctrl = rng.randn(om.nu)
+        om.step(q, v, ctrl, 5, w)
+        st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 8, P(qf), P(vf), P(wf), P(ctrl.astype(np.float32)), 5)
+        assert st == 0 and abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3, t

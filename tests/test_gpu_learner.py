@@ -209,3 +209,64 @@ def test_wide_observation_morphologies_train_step(Dw, Aw):
         assert abs(a_ - b_) <= 1e-4 * abs(b_) + 1e-6, (got, ostats)
     assert abs(g_gpu - ograd).max() <= 2e-4 * abs(ograd).max()
     np.testing.assert_allclose(m.get_flat(), of, atol=2e-6)
+
+
+def test_zoo_opponent_and_eval_loop():
+    """Row N1: policy_zoo tanh MLP (obs filter, separate V net) through the CUDA MLP kernel vs the float64 restatement on synthetic
+    parameters (atol 3e-5) and, when the reference asset is present, on agent-params-v3.npy against the committed golden;
+    then the evaluation loop of eval_robosumo_against_fix.py on a small device env (adjust_z = -0.5)."""
+    import torch
+    from oracle import ppo_oracle as po
+    from robosumo_selfplay_b200.policy_zoo import ZooMLPPolicy, evaluate_against_fixed
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    rng = np.random.RandomState(0)
+    Dz, Az = 120, 8
+    n = 3 + 2 * Dz + 1 + 2 * (Dz * 64 + 64 + 64 * 64 + 64) + 64 + 1 + 64 * Az + Az + Az
+    flat = (rng.randn(n) * 0.2).astype(np.float32)
+    flat[0:3] = [5.0, 80.0, 10.0]; flat[3:3 + Dz] = rng.randn(Dz) * 3; flat[3 + Dz:3 + 2 * Dz] = 20 + rng.rand(Dz) * 30; flat[3 + 2 * Dz] = 10.0
+    obs = rng.randn(200, Dz)
+    zp = ZooMLPPolicy(flat, Dz, Az)
+    a, extra = zp.act(obs, stochastic=False)
+    ra, rv = po.zoo_mlp_act(flat, obs, Dz, Az)
+    np.testing.assert_allclose(a, ra, atol=3e-5); np.testing.assert_allclose(extra['vpred'], rv, atol=1e-4)
+    g = np.load(os.path.join(GOLD, 'zoo_ant_v3.npz'))
+    path = '/root/reference/robosumo/robosumo/policy_zoo/assets/ant/mlp/agent-params-v3.npy'
+    if os.path.exists(path):
+        zp3 = ZooMLPPolicy.load(path, Dz, Az)
+        a3, e3 = zp3.act(g['obs'], stochastic=False)
+        np.testing.assert_allclose(a3, g['act'], atol=5e-5); np.testing.assert_allclose(e3['vpred'], g['vpred'], rtol=1e-4, atol=1e-3)
+        zp = zp3
+    env = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=64, seed=3, device_api=True, adjust_z=-0.5, timestep_limit=40)
+    np.random.seed(0)
+    model = PPOModel(ob_dim=121, ac_dim=8, trainable=False)
+    res = evaluate_against_fixed(env, model, zp, rounds=64)
+    assert res['rounds'] >= 64 and abs(res['win'] + res['draw'] + res['lose'] - 1.0) < 1e-9
+
+
+def test_mixed_morphology_pair_physics(oracle_models):
+    """Ant-vs-Bug (robosumo/__init__.py:19-29): ragged observations (121 / 165) and actions (8 / 12); 10 env steps vs the oracle."""
+    import torch
+    from oracle.physics import OracleModel, load_model_json
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    om = OracleModel(load_model_json('ant_bug'))
+    rng = np.random.RandomState(4)
+    E = 4
+    q = np.tile(om.qpos0, (E, 1)); v = np.zeros((E, om.nv)); w = np.zeros((E, om.nv))
+    for e in range(E):
+        phi = rng.uniform(0, 2 * np.pi)
+        for a_, o_ in ((0, 0), (1, 15)):
+            q[e, o_] = 1.15 * np.cos(phi + a_ * np.pi); q[e, o_ + 1] = 1.15 * np.sin(phi + a_ * np.pi); q[e, o_ + 2] = 1.25
+        q[e] += rng.uniform(-.1, .1, om.nq); v[e] = 0.1 * rng.randn(om.nv); om.normalize_qpos(q[e])
+    env = B200SumoVecEnv('RoboSumo-Ant-vs-Bug-v0', num_envs=E, seed=1, device_api=True, auto_reset=False)
+    assert env.mixed and env.obs_dims == (121, 165) and env.act_dims == (8, 12)
+    oa, ob = env.set_state(q, v)
+    assert oa.shape == (E, 121) and ob.shape == (E, 165)
+    for t in range(10):
+        a0, a1 = rng.randn(E, 8), rng.randn(E, 12)
+        (oa, ob), rew, done, _ = env.step((torch.as_tensor(a0, dtype=torch.float32, device='cuda'), torch.as_tensor(a1, dtype=torch.float32, device='cuda')))
+        for e in range(E):
+            om.step(q[e], v[e], np.concatenate([a0[e], a1[e]]), 5, w[e])
+        gq, gv, _, _ = env.get_state()
+        assert abs(gq.cpu().numpy() - q).max() < 2e-4 and abs(gv.cpu().numpy() - v).max() < 5e-3, t
+    assert torch.equal(oa[:, :15], gq[:, :15]) and torch.equal(ob[:, :19], gq[:, 15:34]) and torch.equal(oa[:, 107:114], gq[:, 15:22])

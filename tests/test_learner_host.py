@@ -99,3 +99,19 @@ def test_gloo_world2_allreduce_and_broadcast():
     for rank, buf, want, snap in res:
         np.testing.assert_allclose(buf[:5], want, rtol=1e-12)
         assert buf[5] == 256 and (snap == 0).all()
+
+
+def test_zoo_golden_matches_reference_asset():
+    """tests/golden/zoo_ant_v3.npz was computed from the reference's agent-params-v3.npy: same size / checksum, and the float64
+    restatement of policy_zoo/policy.py reproduces the stored outputs."""
+    import hashlib
+    from oracle.ppo_oracle import zoo_mlp_act
+    g = np.load(os.path.join(GOLD, 'zoo_ant_v3.npz'))
+    assert int(g['size']) == 24645
+    path = '/root/reference/robosumo/robosumo/policy_zoo/assets/ant/mlp/agent-params-v3.npy'
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present on this box")
+    flat = np.load(path)
+    assert hashlib.sha256(flat.tobytes()).hexdigest() == str(g['sha256'])
+    act, v = zoo_mlp_act(flat, g['obs'], 120, 8)
+    np.testing.assert_allclose(act, g['act'], atol=1e-12); np.testing.assert_allclose(v, g['vpred'], atol=1e-9)
