@@ -102,7 +102,7 @@ __device__ __forceinline__ void load_state(Ctx<LA, LB>& c, const EnvDev& d, int 
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NQ) { s.q[i] = d.qpos[(size_t)e * S::NQ + i]; }
     RS_LANE_LOOP(i, S::NV) { s.v[i] = d.qvel[(size_t)e * S::NV + i]; s.x[i] = d.warm[(size_t)e * S::NV + i]; }
-    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; s.max_iter = 0; }
+    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; s.max_iter = 0; s.nprev = 0; }
     RS_SYNC();
 }
 template <int LA, int LB>

@@ -121,7 +121,7 @@ struct Slab {
     float Rt[2][9];   // torso rotation matrices
     float org[NB][3]; // body origins: [a] torso a, [2+g] hip of leg g, [2+LT+g] ankle of leg g
     float tip[LT][3];
-    float axh[LT][3], axa[LT][3];   // joint axes in world
+    float axa[LT][3];               // ankle axes in world (hip axes are fixed in the torso: recomputed as R_t * ax_hip)
     // joint-space inertia, arrowhead form: root 6x6 per agent, root-leg coupling 6x2 and leg 2x2 (hh, ha, aa) per leg
     float Mr[2][36], Mc[LT][12], Ml[LT][3];
     float H[HDED];
@@ -136,7 +136,9 @@ struct Slab {
     // ---- contacts: position, normal, first tangent (second = n x t1), D, rows ----
     float cpos[MAXC][3], cn[MAXC][3], ct1[MAXC][3], cD[MAXC];
     float caref[MAXC][4], cjar[MAXC][4];          // (dynamics() borrows these two as leg-inertia scratch)
-    int cbody[MAXC];                               // (bA + 1) | (bB + 1) << 8 ; -1 = world
+    int cbody[MAXC];                               // (bA + 1) | (bB + 1) << 8 | key << 16 | active rows << 28 ; body -1 = world
+    unsigned short cprev[MAXC];                    // contacts of the previous evaluation: key << 4 | final active rows
+    int nprev;
     // joint limits (one potential row per hinge)
     float lsgn[NU], lD[NU], laref[NU], ljar[NU];
     float scr[64];                  // per-contact direction Jacobians: idx(16 as float) + 3 x 16
@@ -145,7 +147,10 @@ struct Slab {
     int tot_iter, tot_coupled, tot_ncon, max_iter;      // diagnostics accumulated over one env step
     RS_HD float* legI(int g) { return &caref[0][0] + 10 * g; }
     RS_HD int bA(int k) const { return (cbody[k] & 255) - 1; }
-    RS_HD int bB(int k) const { return (cbody[k] >> 8) - 1; }
+    RS_HD int bB(int k) const { return ((cbody[k] >> 8) & 255) - 1; }
+    RS_HD int ckey(int k) const { return (cbody[k] >> 16) & 4095; }
+    RS_HD int cact(int k) const { return (cbody[k] >> 28) & 15; }
+    RS_HD void set_cact(int k, int bits) { cbody[k] = (cbody[k] & 0x0FFFFFFF) | (bits << 28); }
     // index of H(ir, ic); in block-diagonal mode ir and ic belong to the same agent
     RS_HD int hidx(int ir, int ic) const {
         if (coupled) return ir * NVP + ic;
@@ -168,6 +173,7 @@ struct Ctx {
     RS_HD int agent_of_leg(int g) const { return g >= LA ? 1 : 0; }
     RS_HD int hipdof(int g) const { int a = agent_of_leg(g); return vadr(a) + 6 + 2 * (g - leg0(a)); }
     RS_HD int hipq(int g) const { int a = agent_of_leg(g); return qadr(a) + 7 + 2 * (g - leg0(a)); }
+    RS_HD V3 hip_axis(int g) const { int a = agent_of_leg(g); return mulR(s->Rt[a], ld3(am[a].ax_hip[g - leg0(a)])); }
     RS_HD int bhip(int g) const { return 2 + g; }
     RS_HD int bank(int g) const { return 2 + S::LT + g; }
 };
@@ -207,7 +213,6 @@ RS_HD void fk(Ctx<LA, LB>& c) {
         st3(s.org[c.bhip(g)], ph);
         st3(s.org[c.bank(g)], pa);
         st3(s.tip[g], pa + mulR(R, tipl));
-        st3(s.axh[g], mulR(R, axh));
         st3(s.axa[g], mulR(R, rot(axh, sh, ch, axa)));
     }
     RS_SYNC();
@@ -258,7 +263,7 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         const float* R = s.Rt[a];
         int va = c.vadr(a), dh = c.hipdof(g), da = dh + 1;
         V3 O = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]) - O, pa = ld3(s.org[c.bank(g)]) - O, pt = ld3(s.tip[g]) - O;
-        V3 axh = ld3(s.axh[g]), axa = ld3(s.axa[g]);
+        V3 axh = c.hip_axis(g), axa = ld3(s.axa[g]);
         float len;
         Cap hip, ank;
         hip.m = m.m_hip[l]; hip.ip = m.ip_hip[l]; hip.ia = m.ia_hip[l]; hip.c = 0.5f * (ph + pa); hip.u = normalized(pa - ph, &len);
@@ -377,13 +382,13 @@ RS_HD V3 make_frame_y(V3 n, V3 yhint) {   // mju_makeFrame: second axis (third =
 }
 
 template <int LA, int LB>
-RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n, V3 yhint, float tran) {
+RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n, V3 yhint, float tran, int key) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
     if (!(dist < RS_MARGIN)) return;
     int k = RS_ATOMIC_INC(&s.ncon);
     if (k >= S::MAXC) return;      // counted, dropped: status flag raised by the caller
-    s.cbody[k] = (bA + 1) | ((bB + 1) << 8);
+    s.cbody[k] = (bA + 1) | ((bB + 1) << 8) | ((key & 4095) << 16);     // key: stable identity of this geom pair across evaluations
     s.cD[k] = dist; s.caref[k][0] = tran;      // parked here until make_constraints turns them into D and aref
     if (bA >= 0 && ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT)))) s.coupled = 1;
     st3(s.cpos[k], pos);
@@ -392,11 +397,11 @@ RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n,
 
 // sphere (centre cA, radius rA, side A) against sphere (cB, rB, side B): normal A -> B
 template <int LA, int LB>
-RS_HD void sph_sph(Ctx<LA, LB>& c, int bA, int bB, V3 cA, float rA, V3 cB, float rB, float tran) {
+RS_HD void sph_sph(Ctx<LA, LB>& c, int bA, int bB, V3 cA, float rA, V3 cB, float rB, float tran, int key) {
     float len;
     V3 n = normalized(cB - cA, &len);
     float dist = len - rA - rB;
-    if (dist < RS_MARGIN) add_contact(c, bA, bB, dist, cA + (rA + 0.5f * dist) * n, n, v3(0, 0, 0), tran);
+    if (dist < RS_MARGIN) add_contact(c, bA, bB, dist, cA + (rA + 0.5f * dist) * n, n, v3(0, 0, 0), tran, key);
 }
 RS_HD V3 seg_nearest(V3 e0, V3 e1, V3 p) {
     V3 d = e1 - e0;
@@ -442,11 +447,11 @@ RS_HD void geom_of(const Ctx<LA, LB>& c, int i, V3* e0, V3* e1, float* r, int* b
 }
 
 template <int LA, int LB>
-RS_HD void sphere_vs_world(Ctx<LA, LB>& c, int body, V3 p, float r, float iw, V3 yhint, bool rails, bool floor_too) {
+RS_HD void sphere_vs_world(Ctx<LA, LB>& c, int body, V3 p, float r, float iw, V3 yhint, int key, bool floor_too) {
     // floor plane z = RS_FLOOR_Z, normal +z
     if (floor_too) {
         float dist = p.z - RS_FLOOR_Z - r;
-        if (dist < RS_MARGIN) add_contact(c, -1, body, dist, v3(p.x, p.y, p.z - r - 0.5f * dist), v3(0.f, 0.f, 1.f), yhint, iw);
+        if (dist < RS_MARGIN) add_contact(c, -1, body, dist, v3(p.x, p.y, p.z - r - 0.5f * dist), v3(0.f, 0.f, 1.f), yhint, iw, key);
     }
     // tatami box: centre (0,0,RS_BOX_CZ), half (RS_BOX_HX, RS_BOX_HX, RS_BOX_HZ)
     {
@@ -457,7 +462,7 @@ RS_HD void sphere_vs_world(Ctx<LA, LB>& c, int body, V3 p, float r, float iw, V3
             float len;
             V3 n = normalized(loc - cl, &len);     // from box to sphere
             float dist = len - r;
-            if (dist < RS_MARGIN) add_contact(c, -1, body, dist, v3(cl.x, cl.y, cl.z + RS_BOX_CZ) + (0.5f * dist) * n, n, v3(0, 0, 0), iw);
+            if (dist < RS_MARGIN) add_contact(c, -1, body, dist, v3(cl.x, cl.y, cl.z + RS_BOX_CZ) + (0.5f * dist) * n, n, v3(0, 0, 0), iw, key + 1);
         } else {
             float px = RS_BOX_HX - fabsf(loc.x), py = RS_BOX_HX - fabsf(loc.y), pz = RS_BOX_HZ - fabsf(loc.z);
             V3 n; float best;
@@ -465,10 +470,9 @@ RS_HD void sphere_vs_world(Ctx<LA, LB>& c, int body, V3 p, float r, float iw, V3
             else if (py <= pz) { best = py; n = v3(0.f, loc.y >= 0.f ? 1.f : -1.f, 0.f); }
             else { best = pz; n = v3(0.f, 0.f, loc.z >= 0.f ? 1.f : -1.f); }
             float dist = -best - r;
-            add_contact(c, -1, body, dist, v3(loc.x, loc.y, loc.z + RS_BOX_CZ) + (-r - 0.5f * dist) * n, n, v3(0, 0, 0), iw);
+            add_contact(c, -1, body, dist, v3(loc.x, loc.y, loc.z + RS_BOX_CZ) + (-r - 0.5f * dist) * n, n, v3(0, 0, 0), iw, key + 1);
         }
     }
-    (void)rails;
 }
 
 template <int LA, int LB>
@@ -484,8 +488,9 @@ RS_HD void collide(Ctx<LA, LB>& c) {
         float len = 0.f;
         V3 ax = sph ? v3(0, 0, 0) : normalized(e1 - e0, &len);
         // MuJoCo's capsule geom frame has z = from - to; the plane-capsule routine emits the +z end first
-        sphere_vs_world(c, body, sph ? e0 : e0, r, iw, ax, true, true);
-        if (!sph) sphere_vs_world(c, body, e1, r, iw, ax, true, true);
+        // keys: geom i owns 12 slots: end0 {floor, box}, end1 {floor, box}, rails 4..7; pair contacts start at 12 * NG
+        sphere_vs_world(c, body, e0, r, iw, ax, 12 * i, true);
+        if (!sph) sphere_vs_world(c, body, e1, r, iw, ax, 12 * i + 2, true);
         // rails (thin cylinders treated as capsules of radius RS_RAIL_R)
         float mx = fmaxf(fabsf(e0.x), fabsf(e1.x)) + r + RS_MARGIN + RS_RAIL_R;
         float my = fmaxf(fabsf(e0.y), fabsf(e1.y)) + r + RS_MARGIN + RS_RAIL_R;
@@ -498,7 +503,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                 V3 pg, pr;
                 if (sph) { pg = e0; pr = seg_nearest(rp - RS_RAIL * ra, rp + RS_RAIL * ra, e0); }
                 else seg_seg(0.5f * (e0 + e1), ax, 0.5f * len, rp, ra, RS_RAIL, &pg, &pr);
-                sph_sph(c, -1, body, pr, RS_RAIL_R, pg, r, iw);
+                sph_sph(c, -1, body, pr, RS_RAIL_R, pg, r, iw, 12 * i + 4 + k);
             }
         }
     }
@@ -525,7 +530,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                     else if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
                     else if (sB) { pB = b0; pA = seg_nearest(a0, a1, b0); }
                     else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
-                    sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB);
+                    sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB, 12 * S::NG + p);
                 }
             }
         }
@@ -562,7 +567,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                 V3 pA, pB;
                 if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
                 else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
-                sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB);
+                sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB, 12 * S::NG + S::NGA * S::NGB + a * 512 + p);
             }
         }
     }
@@ -586,7 +591,7 @@ RS_HD void twists(Ctx<LA, LB>& c, const float* vec) {
         V3 pt = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]), pa = ld3(s.org[c.bank(g)]);
         int dh = c.hipdof(g);
         V3 vh = vt + cross(wt, ph - pt);
-        V3 wh = wt + vec[dh] * ld3(s.axh[g]);
+        V3 wh = wt + vec[dh] * c.hip_axis(g);
         V3 vk = vh + cross(wh, pa - ph);
         V3 wk = wh + vec[dh + 1] * ld3(s.axa[g]);
         st3(s.tw[c.bhip(g)], wh); st3(s.tw[c.bhip(g)] + 3, vh);
@@ -680,9 +685,10 @@ RS_HD void jt_forces(Ctx<LA, LB>& c) {
     RS_SYNC();
     RS_LANE_LOOP(k, s.ncon) {
         float D = s.cD[k], f[4];
-        for (int r = 0; r < 4; r++) { float j = s.cjar[k][r]; f[r] = j < 0.f ? -D * j : 0.f; }
+        const int act = s.cact(k);
+        for (int r = 0; r < 4; r++) f[r] = ((act >> r) & 1) ? -D * s.cjar[k][r] : 0.f;
         float fn = f[0] + f[1] + f[2] + f[3];
-        if (fn > 0.f) {
+        if (act != 0) {
             V3 cn_ = ld3(s.cn[k]), ct_ = ld3(s.ct1[k]);
             V3 F = fn * cn_ + (RS_MU * (f[0] - f[1])) * ct_ + (RS_MU * (f[2] - f[3])) * cross(cn_, ct_);
             V3 p = ld3(s.cpos[k]);
@@ -705,7 +711,7 @@ RS_HD void jt_forces(Ctx<LA, LB>& c) {
         V3 Th = ld3(s.wr[c.bhip(g)]) + Ta + cross(pa - ph, Fa);
         float fl_h = ((s.lmask >> (2 * g)) & 1) ? -s.lD[2 * g] * s.ljar[2 * g] : 0.f;
         float fl_a = ((s.lmask >> (2 * g + 1)) & 1) ? -s.lD[2 * g + 1] * s.ljar[2 * g + 1] : 0.f;
-        s.jtf[dh] = dot(ld3(s.axh[g]), Th) + s.lsgn[2 * g] * fl_h;
+        s.jtf[dh] = dot(c.hip_axis(g), Th) + s.lsgn[2 * g] * fl_h;
         s.jtf[dh + 1] = dot(ld3(s.axa[g]), Ta) + s.lsgn[2 * g + 1] * fl_a;
         st3(s.legF[g], Th); st3(s.legF[g] + 3, Fh);     // about the hip origin
     }
@@ -750,7 +756,7 @@ RS_HD void side_entry(const Ctx<LA, LB>& c, int b, int k, V3 p, V3 dir, bool ski
         V3 col = v3(R[e], R[3 + e], R[6 + e]);
         *idx = va + k; *val = dot(col, cross(p - ld3(s.org[a]), dir));
     } else if (k == 6 && depth >= 1) {
-        *idx = c.hipdof(g); *val = dot(ld3(s.axh[g]), cross(p - ld3(s.org[c.bhip(g)]), dir));
+        *idx = c.hipdof(g); *val = dot(c.hip_axis(g), cross(p - ld3(s.org[c.bhip(g)]), dir));
     } else if (k == 7 && depth >= 2) {
         *idx = c.hipdof(g) + 1; *val = dot(ld3(s.axa[g]), cross(p - ld3(s.org[c.bank(g)]), dir));
     }
@@ -784,8 +790,8 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
     RS_SYNC();
     const int ncon = s.ncon;
     for (int k = 0; k < ncon; k++) {
-        float a0 = s.cjar[k][0] < 0.f ? 1.f : 0.f, a1 = s.cjar[k][1] < 0.f ? 1.f : 0.f;
-        float a2 = s.cjar[k][2] < 0.f ? 1.f : 0.f, a3 = s.cjar[k][3] < 0.f ? 1.f : 0.f;
+        const int act = s.cact(k);
+        float a0 = (float)(act & 1), a1 = (float)((act >> 1) & 1), a2 = (float)((act >> 2) & 1), a3 = (float)((act >> 3) & 1);
         float na = a0 + a1 + a2 + a3;
         if (na == 0.f) continue;       // uniform across the warp (shared data)
         float D = s.cD[k];
@@ -975,7 +981,15 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         rows_of(c, vec, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
         mat_vec(c, vec, first ? s.r : s.Md, first ? s.r : (const float*)0);     // first: r = M x0 - qfrc_smooth
         if (first) {
-            RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] -= s.caref[k][r]; }
+            RS_LANE_LOOP(k, s.ncon) {
+                // rows of the same geom pair at the previous evaluation's solution predict this evaluation's active rows
+                int bits = 16;
+                const int key = s.ckey(k);
+                for (int q = 0; q < s.nprev; q++) if ((s.cprev[q] >> 4) == key) bits = s.cprev[q] & 15;
+                int sign = 0;
+                for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
+                s.set_cact(k, bits < 16 ? bits : sign);
+            }
             RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
             if (RS_LANE0) s.lmask = s.pmask & s.pvalid;
             RS_SYNC();
@@ -987,7 +1001,8 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         if (RS_LANE0) s.same = 1;
         RS_SYNC();
         RS_LANE_LOOP(k, s.ncon) {
-            for (int r = 0; r < 4; r++) if ((s.cjar[k][r] < 0.f) != (s.cjar[k][r] + s.cjd[k][r] < 0.f)) s.same = 0;
+            const int act = s.cact(k);
+            for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] + s.cjd[k][r] < 0.f)) s.same = 0;
         }
         RS_LANE_LOOP(j, S::NU) {
             if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
@@ -996,6 +1011,10 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         if (RS_LANE0) s.pvalid = 0;
         RS_SYNC();
         RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] < 0.f))) s.pvalid = 1; }
+        RS_LANE_LOOP(k, s.ncon) {
+            const int act = s.cact(k);
+            for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] < 0.f)) s.pvalid = 1;
+        }
         RS_SYNC();
         const int same = s.same, predicted = s.pvalid;
         float alpha = 1.f;
@@ -1016,7 +1035,11 @@ RS_HD void solve(Ctx<LA, LB>& c) {
             }
         }
         RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; }
-        RS_LANE_LOOP(k, s.ncon) { for (int r = 0; r < 4; r++) s.cjar[k][r] += alpha * s.cjd[k][r]; }
+        RS_LANE_LOOP(k, s.ncon) {
+            int sign = 0;
+            for (int r = 0; r < 4; r++) { s.cjar[k][r] += alpha * s.cjd[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
+            s.set_cact(k, sign);             // sign set at the new point
+        }
         RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
         if (RS_LANE0) s.lmask = 0;
         RS_SYNC();
@@ -1025,6 +1048,8 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         it++;
         if (same) conv = true;
     }
+    RS_LANE_LOOP(k, s.ncon) { s.cprev[k] = (unsigned short)((s.ckey(k) << 4) | s.cact(k)); }
+    if (RS_LANE0) s.nprev = s.ncon;
     if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled; s.tot_ncon += s.ncon; if (it > s.max_iter) s.max_iter = it; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
     RS_SYNC();
 }
