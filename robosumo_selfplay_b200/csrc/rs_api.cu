@@ -21,6 +21,11 @@
 #ifndef RS_SYNC_GROUP
 #define RS_SYNC_GROUP 7
 #endif
+#ifdef RS_EXPERIMENT_CLOCK
+__device__ long long rs_dbg[4200 * 128];
+extern "C" int rs_debug_read(void* dst, size_t bytes) { return (int)cudaMemcpyFromSymbol(dst, rs_dbg, bytes); }
+#endif
+__device__ __forceinline__ long long rs_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 #if defined(__CUDA_ARCH__)
 #if RS_SYNC_MODE == 1
 #define RS_EVAL_SYNC() __syncthreads()
@@ -31,6 +36,32 @@
 #elif RS_SYNC_MODE == 5
 #define RS_EVAL_SYNC() __syncthreads()
 #define RS_SOLVE_SYNC() __syncthreads()
+#elif RS_SYNC_MODE == 6
+// sliding window: a warp may run at most one evaluation ahead of the slowest warp of its block (two mbarriers, one per parity)
+#define RS_EVAL_SYNC() rs_window_sync(c.evk)
+__device__ __forceinline__ unsigned long long* rs_win_bars() { __shared__ unsigned long long b[2]; return b; }
+__device__ __forceinline__ void rs_window_init() {
+    if (threadIdx.x == 0) {
+        unsigned long long* b = rs_win_bars();
+        for (int i = 0; i < 2; i++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(b + i)), "r"(blockDim.x >> 5));
+    }
+}
+__device__ __forceinline__ void rs_window_sync(int& k) {
+    unsigned long long* b = rs_win_bars();
+    if (k >= 1 && (threadIdx.x & 31) == 0) {
+        unsigned long long st;
+        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((unsigned)__cvta_generic_to_shared(b + ((k - 1) & 1))) : "memory");
+    }
+    if (k >= 2) {
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(b + (k & 1)), par = ((k - 2) >> 1) & 1;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\tWW_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+            "@P1 bra WD_%=;\n\tbra WW_%=;\n\tWD_%=:\n\t}" :: "r"(addr), "r"(par) : "memory");
+    }
+    k++;
+}
 #elif RS_SYNC_MODE == 3
 #define RS_EVAL_SYNC() rs_group_sync()
 __device__ __forceinline__ void rs_group_sync() {
@@ -38,6 +69,12 @@ __device__ __forceinline__ void rs_group_sync() {
     const int first = g * RS_SYNC_GROUP, cnt = (nw - first < RS_SYNC_GROUP ? nw - first : RS_SYNC_GROUP) * 32;
     asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "r"(cnt));
 }
+#endif
+#ifdef RS_EXPERIMENT_CLOCK
+#define RS_ACC(i) { __syncwarp(); long long rs_now = rs_clock(); c.acc[i] += rs_now - c.tlast; c.tlast = rs_now; }
+#define RS_CLOCK_BEGIN() { __syncwarp(); if ((threadIdx.x & 31) == 0 && c.evk < 20) rs_dbg[(size_t)c.env * 128 + 3 * c.evk] = rs_clock(); }
+#define RS_CLOCK_MARK(i) { if (i == 2) { __syncwarp(); if ((threadIdx.x & 31) == 0 && c.evk < 20) rs_dbg[(size_t)c.env * 128 + 3 * c.evk + 1] = rs_clock(); } }
+#define RS_CLOCK_END() { __syncwarp(); if ((threadIdx.x & 31) == 0 && c.evk < 20) { rs_dbg[(size_t)c.env * 128 + 3 * c.evk + 2] = rs_clock(); rs_dbg[(size_t)c.env * 128 + 64 + c.evk] = c.s->niter | (c.s->coupled << 8) | (c.s->ncon << 16); } c.evk++; }
 #endif
 #ifdef RS_USE_PHASE_SYNC
 #define RS_PHASE_SYNC() __syncthreads()
@@ -90,6 +127,10 @@ template <int LA, int LB>
 __device__ __forceinline__ Slab<LA, LB>* warp_setup(Ctx<LA, LB>& c, const EnvDev& d, rs_agent_model* sm_am, unsigned char* smem_raw) {
     typedef Slab<LA, LB> S;
     for (int i = threadIdx.x; i < (int)(2 * sizeof(rs_agent_model) / 4); i += blockDim.x) ((int*)sm_am)[i] = ((const int*)d.am)[i];
+#if defined(__CUDA_ARCH__) && RS_SYNC_MODE == 6
+    rs_window_init();
+    c.evk = 0;
+#endif
     __syncthreads();
     S* s = reinterpret_cast<S*>(smem_raw) + (threadIdx.x >> 5);
     c.s = s; c.am = sm_am; c.h = d.h; c.max_newton = d.max_newton;
@@ -195,6 +236,9 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     set_act(c, act);
     float before[4] = { s.q[c.qadr(0)], s.q[c.qadr(0) + 1], s.q[c.qadr(1)], s.q[c.qadr(1) + 1] };
     RS_SYNC();
+#ifdef RS_EXPERIMENT_CLOCK
+    c.evk = 0; c.env = e; for (int i = 0; i < 6; i++) c.acc[i] = 0; c.tlast = rs_clock(); if (lane == 0) rs_dbg[(size_t)e * 128 + 60] = rs_clock();
+#endif
     simulate(c, d.P.frame_skip);
     // mj_checkPos / mj_checkVel analogue
     {
@@ -210,6 +254,9 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     float er = d.ep_ret[e] + o.rew[0], edr = d.ep_dret[e] + o.info[0][6];
     if (!live) return;
     if (lane == 0) { d.diag[4 * e] = s.tot_iter; d.diag[4 * e + 1] = s.tot_coupled; d.diag[4 * e + 2] = s.tot_ncon; d.diag[4 * e + 3] = s.max_iter; }
+#ifdef RS_EXPERIMENT_CLOCK
+    if (lane == 0) { rs_dbg[(size_t)e * 128 + 61] = rs_clock(); for (int i = 0; i < 6; i++) rs_dbg[(size_t)e * 128 + 90 + i] = c.acc[i]; }
+#endif
     if (lane == 0) {
         rew[2 * e] = o.rew[0]; rew[2 * e + 1] = o.rew[1];
         done[2 * e] = (uint8_t)o.done[0]; done[2 * e + 1] = (uint8_t)o.done[1];

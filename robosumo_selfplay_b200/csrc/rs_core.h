@@ -24,6 +24,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "../../include/rs_b200.h"
 
 #if defined(__CUDACC__)
@@ -142,7 +143,8 @@ struct Slab {
     // joint limits (one potential row per hinge)
     float lsgn[NU], lD[NU], laref[NU], ljar[NU];
     float scr[64];                  // per-contact direction Jacobians: idx(16 as float) + 3 x 16
-    int ncon, status, niter, same, coupled;
+    int ncon, status, niter, same;
+    int coupled;                              // bit 0: an inter-agent contact couples the two agents, bit 1: an intra-agent (leg-leg) contact; 0: H keeps M's arrowhead form
     int lmask, pmask, pvalid;                 // limit rows: active set in use / predicted from the previous evaluation / prediction valid
     int tot_iter, tot_coupled, tot_ncon, max_iter;      // diagnostics accumulated over one env step
     RS_HD float* legI(int g) { return &caref[0][0] + 10 * g; }
@@ -153,7 +155,7 @@ struct Slab {
     RS_HD void set_cact(int k, int bits) { cbody[k] = (cbody[k] & 0x0FFFFFFF) | (bits << 28); }
     // index of H(ir, ic); in block-diagonal mode ir and ic belong to the same agent
     RS_HD int hidx(int ir, int ic) const {
-        if (coupled) return ir * NVP + ic;
+        if (coupled & 1) return ir * NVP + ic;
         return ir >= NVA ? BSA + (ir - NVA) * (NVB + 1) + (ic - NVA) : ir * (NVA + 1) + ic;
     }
 };
@@ -166,6 +168,10 @@ struct Ctx {
     const rs_agent_model* am;   // [2]
     float h;                    // timestep
     int max_newton;
+#ifdef RS_EXPERIMENT_CLOCK
+    int env; long long acc[6], tlast;  // developer instrumentation: per-evaluation timestamps, see rs_api.cu
+#endif
+    int evk;                    // evaluations started by this warp (sliding-window re-alignment, device only)
     RS_HD int L(int a) const { return a ? LB : LA; }
     RS_HD int qadr(int a) const { return a ? S::NQA : 0; }
     RS_HD int vadr(int a) const { return a ? S::NVA : 0; }
@@ -390,7 +396,7 @@ RS_HD void add_contact(Ctx<LA, LB>& c, int bA, int bB, float dist, V3 pos, V3 n,
     if (k >= S::MAXC) return;      // counted, dropped: status flag raised by the caller
     s.cbody[k] = (bA + 1) | ((bB + 1) << 8) | ((key & 4095) << 16);     // key: stable identity of this geom pair across evaluations
     s.cD[k] = dist; s.caref[k][0] = tran;      // parked here until make_constraints turns them into D and aref
-    if (bA >= 0 && ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT)))) s.coupled = 1;
+    if (bA >= 0) RS_ATOMIC_OR(&s.coupled, ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1 : 2);
     st3(s.cpos[k], pos);
     st3(s.cn[k], n); st3(s.ct1[k], make_frame_y(n, yhint));
 }
@@ -481,12 +487,17 @@ RS_HD void collide(Ctx<LA, LB>& c) {
     S& s = *c.s;
     if (RS_LANE0) { s.ncon = 0; s.coupled = 0; }
     RS_SYNC();
+    // bounding data of every geom (centre, axis, half length, radius), parked in the H array (dead until build_H): the pair
+    // loops below cull on it and only rebuild the geoms of the few pairs that pass
+    static_assert(10 * S::NG <= S::HDED, "geom cache must fit in the H array");
+    float* gc = s.H;
     // --- agent geoms against the world (floor plane, tatami box, four border rails) ---
     RS_LANE_LOOP(i, S::NG) {
         V3 e0, e1; float r, iw; int body, agent; bool sph;
         geom_of(c, i, &e0, &e1, &r, &body, &iw, &agent, &sph);
         float len = 0.f;
         V3 ax = sph ? v3(0, 0, 0) : normalized(e1 - e0, &len);
+        { float* G = gc + 10 * i; st3(G, 0.5f * (e0 + e1)); st3(G + 3, ax); G[6] = 0.5f * len; G[7] = r; }     // broad-phase cache
         // MuJoCo's capsule geom frame has z = from - to; the plane-capsule routine emits the +z end first
         // keys: geom i owns 12 slots: end0 {floor, box}, end1 {floor, box}, rails 4..7; pair contacts start at 12 * NG
         sphere_vs_world(c, body, e0, r, iw, ax, 12 * i, true);
@@ -507,6 +518,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
             }
         }
     }
+    RS_SYNC();
     // --- agent 0 geoms against agent 1 geoms ---
     {
         V3 dt = ld3(s.org[1]) - ld3(s.org[0]);
@@ -516,20 +528,19 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                 int ia = p / S::NGB, ib = p - ia * S::NGB;
                 // pair geom indices: agent 0 torso = 0, its leg geoms 2..2+3LA ; agent 1 torso = 1, leg geoms after
                 int gi = ia == 0 ? 0 : 1 + ia, gj = ib == 0 ? 1 : 1 + 3 * LA + ib;
-                V3 a0, a1, b0, b1; float rA, rB, iwA, iwB; int bA, bB, agA, agB; bool sA, sB;
-                geom_of(c, gi, &a0, &a1, &rA, &bA, &iwA, &agA, &sA);
-                geom_of(c, gj, &b0, &b1, &rB, &bB, &iwB, &agB, &sB);
-                V3 ca = 0.5f * (a0 + a1), cb = 0.5f * (b0 + b1);
-                float la, lb;
-                V3 ua = normalized(a1 - a0, &la), ub = normalized(b1 - b0, &lb);
-                float bound = 0.5f * (la + lb) + rA + rB + RS_MARGIN;
+                const float* GA = gc + 10 * gi; const float* GB = gc + 10 * gj;
+                V3 ca = ld3(GA), cb = ld3(GB);
+                float bound = GA[6] + GB[6] + GA[7] + GB[7] + RS_MARGIN;
                 V3 dc = cb - ca;
                 if (dot(dc, dc) < bound * bound) {
+                    V3 a0, a1, b0, b1; float rA, rB, iwA, iwB; int bA, bB, agA, agB; bool sA, sB;
+                    geom_of(c, gi, &a0, &a1, &rA, &bA, &iwA, &agA, &sA);
+                    geom_of(c, gj, &b0, &b1, &rB, &bB, &iwB, &agB, &sB);
                     V3 pA, pB;
                     if (sA && sB) { pA = a0; pB = b0; }
                     else if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
                     else if (sB) { pB = b0; pA = seg_nearest(a0, a1, b0); }
-                    else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
+                    else seg_seg(ca, ld3(GA + 3), GA[6], cb, ld3(GB + 3), GB[6], &pA, &pB);
                     sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB, 12 * S::NG + p);
                 }
             }
@@ -555,18 +566,17 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                 gi = t == 0 ? a : 2 + 3 * (c.leg0(a) + t - 1);      // torso sphere or a welded stub capsule
                 gj = 2 + 3 * (c.leg0(a) + l) + 2;                   // ankle capsule
             }
-            V3 a0, a1, b0, b1; float rA, rB, iwA, iwB; int bA, bB, agA, agB; bool sA, sB;
-            geom_of(c, gi, &a0, &a1, &rA, &bA, &iwA, &agA, &sA);
-            geom_of(c, gj, &b0, &b1, &rB, &bB, &iwB, &agB, &sB);
-            V3 ca = 0.5f * (a0 + a1), cb = 0.5f * (b0 + b1);
-            float la, lb;
-            V3 ua = normalized(a1 - a0, &la), ub = normalized(b1 - b0, &lb);
-            float bound = 0.5f * (la + lb) + rA + rB + RS_MARGIN;
+            const float* GA = gc + 10 * gi; const float* GB = gc + 10 * gj;
+            V3 ca = ld3(GA), cb = ld3(GB);
+            float bound = GA[6] + GB[6] + GA[7] + GB[7] + RS_MARGIN;
             V3 dc = cb - ca;
             if (dot(dc, dc) < bound * bound) {
+                V3 a0, a1, b0, b1; float rA, rB, iwA, iwB; int bA, bB, agA, agB; bool sA, sB;
+                geom_of(c, gi, &a0, &a1, &rA, &bA, &iwA, &agA, &sA);
+                geom_of(c, gj, &b0, &b1, &rB, &bB, &iwB, &agB, &sB);
                 V3 pA, pB;
                 if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
-                else seg_seg(ca, ua, 0.5f * la, cb, ub, 0.5f * lb, &pA, &pB);
+                else seg_seg(ca, ld3(GA + 3), GA[6], cb, ld3(GB + 3), GB[6], &pA, &pB);
                 sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB, 12 * S::NG + S::NGA * S::NGB + a * 512 + p);
             }
         }
@@ -681,26 +691,25 @@ template <int LA, int LB>
 RS_HD void jt_forces(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    RS_LANE_LOOP(i, S::NB * 6) { (&s.wr[0][0])[i] = 0.f; }
-    RS_SYNC();
-    RS_LANE_LOOP(k, s.ncon) {
-        float D = s.cD[k], f[4];
-        const int act = s.cact(k);
-        for (int r = 0; r < 4; r++) f[r] = ((act >> r) & 1) ? -D * s.cjar[k][r] : 0.f;
-        float fn = f[0] + f[1] + f[2] + f[3];
-        if (act != 0) {
-            V3 cn_ = ld3(s.cn[k]), ct_ = ld3(s.ct1[k]);
-            V3 F = fn * cn_ + (RS_MU * (f[0] - f[1])) * ct_ + (RS_MU * (f[2] - f[3])) * cross(cn_, ct_);
-            V3 p = ld3(s.cpos[k]);
-            for (int side = 0; side < 2; side++) {
-                int b = side ? s.bB(k) : s.bA(k);
-                if (b < 0) continue;
-                V3 Fs = side ? F : (-1.f) * F;
-                V3 T = cross(p - ld3(s.org[b]), Fs);
-                RS_ATOMIC_ADDF(&s.wr[b][0], T.x); RS_ATOMIC_ADDF(&s.wr[b][1], T.y); RS_ATOMIC_ADDF(&s.wr[b][2], T.z);
-                RS_ATOMIC_ADDF(&s.wr[b][3], Fs.x); RS_ATOMIC_ADDF(&s.wr[b][4], Fs.y); RS_ATOMIC_ADDF(&s.wr[b][5], Fs.z);
-            }
+    // every body gathers the contact forces that act on it (no atomics: fixed summation order, bit-reproducible)
+    RS_LANE_LOOP(b, S::NB) {
+        V3 T = v3(0.f, 0.f, 0.f), F = v3(0.f, 0.f, 0.f);
+        const V3 o = ld3(s.org[b]);
+        RS_UNROLL1
+        for (int k = 0; k < s.ncon; k++) {
+            const int cb = s.cbody[k], act = (cb >> 28) & 15;
+            const bool onB = ((cb >> 8) & 255) - 1 == b;
+            if ((!onB && (cb & 255) - 1 != b) || act == 0) continue;
+            const float D = s.cD[k];
+            const float f0 = (act & 1) ? -D * s.cjar[k][0] : 0.f, f1 = (act & 2) ? -D * s.cjar[k][1] : 0.f;
+            const float f2 = (act & 4) ? -D * s.cjar[k][2] : 0.f, f3 = (act & 8) ? -D * s.cjar[k][3] : 0.f;
+            const V3 cn_ = ld3(s.cn[k]), ct_ = ld3(s.ct1[k]);
+            V3 Fc = (f0 + f1 + f2 + f3) * cn_ + (RS_MU * (f0 - f1)) * ct_ + (RS_MU * (f2 - f3)) * cross(cn_, ct_);
+            if (!onB) Fc = (-1.f) * Fc;
+            T = T + cross(ld3(s.cpos[k]) - o, Fc);
+            F = F + Fc;
         }
+        st3(s.wr[b], T); st3(s.wr[b] + 3, F);
     }
     RS_SYNC();
     RS_LANE_LOOP(g, S::LT) {
@@ -737,29 +746,26 @@ RS_HD void jt_forces(Ctx<LA, LB>& c) {
 // H = M + J^T D_active J, assembled contact by contact
 // ------------------------------------------------------------------------------------------
 template <int LA, int LB>
-RS_HD void side_entry(const Ctx<LA, LB>& c, int b, int k, V3 p, V3 dir, bool skip_root, int* idx, float* val) {
-    // k-th (0..7) dof of the chain of body b and the Jacobian entry of direction `dir` at point p
+RS_HD V3 side_col(const Ctx<LA, LB>& c, int b, int k, V3 p, bool skip_root, int* idx) {
+    // k-th (0..7) dof of the chain of body b: its index and the vector jc with  J(dir) = jc . dir  for a force direction
+    // `dir` applied at point p (translation: e_k; rotation about axis u through o: u x (p - o))
     typedef Slab<LA, LB> S;
     const S& s = *c.s;
-    *idx = -1; *val = 0.f;
-    if (b < 0) return;
+    *idx = -1;
+    if (b < 0) return v3(0.f, 0.f, 0.f);
     int a, g = -1, depth = 0;
     if (b < 2) a = b;
     else if (b < 2 + S::LT) { g = b - 2; a = c.agent_of_leg(g); depth = 1; }
     else { g = b - 2 - S::LT; a = c.agent_of_leg(g); depth = 2; }
-    int va = c.vadr(a);
-    if (k < 6 && skip_root) return;      // both bodies hang off the same floating base: root columns cancel exactly
-    if (k < 3) { *idx = va + k; *val = k == 0 ? dir.x : (k == 1 ? dir.y : dir.z); }
-    else if (k < 6) {
-        const float* R = s.Rt[a];
-        int e = k - 3;
-        V3 col = v3(R[e], R[3 + e], R[6 + e]);
-        *idx = va + k; *val = dot(col, cross(p - ld3(s.org[a]), dir));
-    } else if (k == 6 && depth >= 1) {
-        *idx = c.hipdof(g); *val = dot(c.hip_axis(g), cross(p - ld3(s.org[c.bhip(g)]), dir));
-    } else if (k == 7 && depth >= 2) {
-        *idx = c.hipdof(g) + 1; *val = dot(ld3(s.axa[g]), cross(p - ld3(s.org[c.bank(g)]), dir));
-    }
+    const int va = c.vadr(a);
+    if (k < 6 && skip_root) return v3(0.f, 0.f, 0.f);      // both bodies hang off the same floating base: root columns cancel exactly
+    if (k < 3) { *idx = va + k; return v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f); }
+    V3 u, o;
+    if (k < 6) { const float* R = s.Rt[a]; const int e = k - 3; u = v3(R[e], R[3 + e], R[6 + e]); o = ld3(s.org[a]); *idx = va + k; }
+    else if (k == 6 && depth >= 1) { u = c.hip_axis(g); o = ld3(s.org[c.bhip(g)]); *idx = c.hipdof(g); }
+    else if (k == 7 && depth >= 2) { u = ld3(s.axa[g]); o = ld3(s.org[c.bank(g)]); *idx = c.hipdof(g) + 1; }
+    else return v3(0.f, 0.f, 0.f);
+    return cross(u, p - o);
 }
 
 template <int LA, int LB>
@@ -767,20 +773,23 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
     float* H = s.H;
-    const int hn = s.coupled ? (int)S::HFULL : (int)S::HBD;
+    const int hn = (s.coupled & 1) ? (int)S::HFULL : (int)S::HBD;
     RS_LANE_LOOP(i, hn) { H[i] = 0.f; }
     RS_SYNC();
     // scatter the arrowhead inertia, one row per lane, and the active limit rows (diagonal)
     RS_LANE_LOOP(i, S::NV) {
         const int a = i >= S::NVA ? 1 : 0, va = c.vadr(a), k = i - va;
         if (k < 6) {
+            RS_UNROLL1
             for (int j = 0; j < 6; j++) H[s.hidx(i, va + j)] = s.Mr[a][k * 6 + j];
+            RS_UNROLL1
             for (int l = 0; l < c.L(a); l++) {
                 const int g = c.leg0(a) + l, dh = va + 6 + 2 * l;
                 H[s.hidx(i, dh)] = s.Mc[g][2 * k]; H[s.hidx(i, dh + 1)] = s.Mc[g][2 * k + 1];
             }
         } else {
             const int l = (k - 6) >> 1, isank = (k - 6) & 1, g = c.leg0(a) + l, dh = va + 6 + 2 * l, j = 2 * g + isank;
+            RS_UNROLL1
             for (int kk = 0; kk < 6; kk++) H[s.hidx(i, va + kk)] = s.Mc[g][2 * kk + isank];
             const float lim = ((s.lmask >> j) & 1) ? s.lD[j] : 0.f;
             H[s.hidx(i, dh)] = isank ? s.Ml[g][1] : s.Ml[g][0] + lim;
@@ -804,12 +813,10 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
             int b = side ? bB : bA, bo = side ? bA : bB;
             float sg = side ? 1.f : -1.f;
             V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
-            int idx; float vn, v1, v2;
+            int idx;
             const bool same = bo >= 0 && b >= 0 && ((bo < 2 ? bo : c.agent_of_leg((bo - 2) % S::LT)) == (b < 2 ? b : c.agent_of_leg((b - 2) % S::LT)));
-            side_entry(c, b, kk, p, n, same, &idx, &vn);
-            side_entry(c, b, kk, p, t1, same, &idx, &v1);
-            side_entry(c, b, kk, p, cross(n, t1), same, &idx, &v2);
-            sc[e] = (float)idx; sc[16 + e] = sg * vn; sc[32 + e] = sg * v1; sc[48 + e] = sg * v2;
+            const V3 jc = sg * side_col(c, b, kk, p, same, &idx);
+            sc[e] = (float)idx; sc[16 + e] = dot(jc, n); sc[32 + e] = dot(jc, t1); sc[48 + e] = dot(jc, cross(n, t1));
         }
         RS_SYNC();
         int lo = bA < 0 ? 8 : 0;       // world side contributes nothing
@@ -838,7 +845,7 @@ template <int LA, int LB>
 RS_HD void chol_solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    const bool bd = !s.coupled;
+    const bool bd = !(s.coupled & 1);
     const int nk = bd ? (S::NVA > S::NVB ? S::NVA : S::NVB) : S::NV;
     RS_LANE_LOOP(j, S::NV) { s.d[j] = -s.d[j]; }
     RS_SYNC();
@@ -858,6 +865,137 @@ RS_HD void chol_solve(Ctx<LA, LB>& c) {
         RS_SYNC();
     }
     RS_LANE_LOOP(j, S::NV) { s.d[j] = s.d[j] * RS_RCP(fmaxf(s.H[s.hidx(j, j)], 1e-12f)); }
+    RS_SYNC();
+}
+
+// ---- arrowhead fast path -----------------------------------------------------------------------------------------------
+// With world contacts only, every row of J touches one floating base and at most one leg, so H = M + J^T D J keeps M's
+// arrowhead form per agent:  [ A  B ; B^T  Dg ]  with A 6x6, B_g 6x2 and Dg_g 2x2 per leg.  It is assembled in that compact
+// form (same layout as Mr | Mc | Ml) and solved by eliminating the legs first:
+//   S = A - sum_g B_g Dg_g^-1 B_g^T,   S d_t = rhs_t - sum_g B_g Dg_g^-1 rhs_g,   d_g = Dg_g^-1 rhs_g - (B_g Dg_g^-1)^T d_t.
+template <int LA, int LB>
+struct Arrow {
+    typedef Slab<LA, LB> S;
+    enum { A0 = 0, B0 = 72, D0 = 72 + 12 * S::LT, NCOPY = 72 + 15 * S::LT, W0 = NCOPY, Y0 = W0 + 12 * S::LT, S0 = Y0 + 2 * S::LT, END = S0 + 84 };
+    static_assert(END <= S::HDED, "compact arrowhead H must fit in the H array");
+    static_assert(offsetof(S, Ml) - offsetof(S, Mr) == (72 + 12 * S::LT) * sizeof(float), "Mr | Mc | Ml must be contiguous");
+};
+
+template <int LA, int LB>
+RS_HD void build_H_arrow(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    typedef Arrow<LA, LB> AR;
+    S& s = *c.s;
+    float* H = s.H;
+    RS_LANE_LOOP(i, (int)AR::NCOPY) { H[i] = (&s.Mr[0][0])[i]; }
+    RS_SYNC();
+    RS_LANE_LOOP(j, S::NU) { if ((s.lmask >> j) & 1) H[AR::D0 + 3 * (j >> 1) + 2 * (j & 1)] += s.lD[j]; }
+    RS_SYNC();
+    const int ncon = s.ncon;
+    for (int k = 0; k < ncon; k++) {
+        const int act = s.cact(k);
+        float a0 = (float)(act & 1), a1 = (float)((act >> 1) & 1), a2 = (float)((act >> 2) & 1), a3 = (float)((act >> 3) & 1);
+        float na = a0 + a1 + a2 + a3;
+        if (na == 0.f) continue;       // uniform across the warp (shared data)
+        float D = s.cD[k];
+        float cnn = D * na, cn1 = RS_MU * D * (a0 - a1), c11 = RS_MU * RS_MU * D * (a0 + a1);
+        float cn2 = RS_MU * D * (a2 - a3), c22 = RS_MU * RS_MU * D * (a2 + a3);
+        float* sc = s.scr;
+        const int b = s.bB(k) >= 0 ? s.bB(k) : s.bA(k);      // the other side is the world
+        RS_LANE_LOOP(e, 8) {
+            V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
+            int idx;
+            const V3 jc = side_col(c, b, e, p, false, &idx);
+            sc[e] = (float)idx; sc[16 + e] = dot(jc, n); sc[32 + e] = dot(jc, t1); sc[48 + e] = dot(jc, cross(n, t1));
+        }
+        RS_SYNC();
+        const int g = b < 2 ? -1 : (b - 2) % S::LT, a = b < 2 ? b : c.agent_of_leg(g);
+        RS_LANE_LOOP(e, 64) {
+            const int r = e >> 3, cc = e & 7;
+            if (r <= cc && sc[r] >= 0.f && sc[cc] >= 0.f) {
+                float nr = sc[16 + r], nc = sc[16 + cc], t1r = sc[32 + r], t1c = sc[32 + cc], t2r = sc[48 + r], t2c = sc[48 + cc];
+                float val = cnn * nr * nc + cn1 * (nr * t1c + t1r * nc) + c11 * t1r * t1c + cn2 * (nr * t2c + t2r * nc) + c22 * t2r * t2c;
+                if (cc < 6) { H[AR::A0 + a * 36 + r * 6 + cc] += val; if (r != cc) H[AR::A0 + a * 36 + cc * 6 + r] += val; }
+                else if (r < 6) H[AR::B0 + 12 * g + 2 * r + (cc - 6)] += val;
+                else H[AR::D0 + 3 * g + (r - 6) + (cc - 6)] += val;
+            }
+        }
+        RS_SYNC();
+    }
+}
+
+// s.d = -H^-1 s.d for the compact arrowhead H of build_H_arrow
+template <int LA, int LB>
+RS_HD void arrow_solve(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    typedef Arrow<LA, LB> AR;
+    S& s = *c.s;
+    float* H = s.H;
+    RS_LANE_LOOP(g, S::LT) {
+        const float* Dg = H + AR::D0 + 3 * g; const float* B = H + AR::B0 + 12 * g;
+        float* W = H + AR::W0 + 12 * g;
+        const float idet = RS_RCP(fmaxf(Dg[0] * Dg[2] - Dg[1] * Dg[1], 1e-20f));
+        const float i00 = Dg[2] * idet, i01 = -Dg[1] * idet, i11 = Dg[0] * idet;
+        for (int k = 0; k < 6; k++) { W[2 * k] = B[2 * k] * i00 + B[2 * k + 1] * i01; W[2 * k + 1] = B[2 * k] * i01 + B[2 * k + 1] * i11; }
+        const int dh = c.hipdof(g);
+        const float gh = -s.d[dh], ga = -s.d[dh + 1];
+        H[AR::Y0 + 2 * g] = i00 * gh + i01 * ga; H[AR::Y0 + 2 * g + 1] = i01 * gh + i11 * ga;
+    }
+    RS_SYNC();
+    // Schur complement onto the floating base, upper triangle + right-hand side (27 entries per agent), mirrored
+    RS_LANE_LOOP(e, 54) {
+        const int a = e >= 27 ? 1 : 0, t = e - 27 * a;
+        int r = 0, cc = t;                                   // t -> (r, cc) with r <= cc <= 6: rows of length 7, 6, 5, ...
+        while (cc >= 7 - r) { cc -= 7 - r; r++; }
+        cc += r;
+        float acc;
+        const int l0 = c.leg0(a), va = c.vadr(a);
+        if (cc < 6) {
+            acc = H[AR::A0 + a * 36 + r * 6 + cc];
+            RS_UNROLL1
+            for (int l = 0; l < c.L(a); l++) {
+                const float* W = H + AR::W0 + 12 * (l0 + l); const float* B = H + AR::B0 + 12 * (l0 + l);
+                acc -= W[2 * r] * B[2 * cc] + W[2 * r + 1] * B[2 * cc + 1];
+            }
+            H[AR::S0 + a * 42 + r * 7 + cc] = acc; H[AR::S0 + a * 42 + cc * 7 + r] = acc;
+        } else {
+            acc = -s.d[va + r];
+            RS_UNROLL1
+            for (int l = 0; l < c.L(a); l++) {
+                const float* Y = H + AR::Y0 + 2 * (l0 + l); const float* B = H + AR::B0 + 12 * (l0 + l);
+                acc -= B[2 * r] * Y[0] + B[2 * r + 1] * Y[1];
+            }
+            H[AR::S0 + a * 42 + r * 7 + 6] = acc;
+        }
+    }
+    RS_SYNC();
+    // 6x6 Gauss-Jordan per agent, row per lane (12 lanes)
+    for (int k = 0; k < 6; k++) {
+        RS_LANE_LOOP(j, 12) {
+            const int a = j >= 6 ? 1 : 0, jr = j - 6 * a;
+            if (jr != k) {
+                const float* prow = H + AR::S0 + a * 42 + k * 7;
+                float* jrow = H + AR::S0 + a * 42 + jr * 7;
+                const float f = jrow[k] * RS_RCP(fmaxf(prow[k], 1e-12f));
+                for (int cc = k + 1; cc < 7; cc++) jrow[cc] = fmaf(-f, prow[cc], jrow[cc]);
+            }
+        }
+        RS_SYNC();
+    }
+    RS_LANE_LOOP(j, 12) {
+        const int a = j >= 6 ? 1 : 0, jr = j - 6 * a;
+        float* row = H + AR::S0 + a * 42 + jr * 7;
+        const float v = row[6] * RS_RCP(fmaxf(row[jr], 1e-12f));
+        row[6] = v; s.d[c.vadr(a) + jr] = v;
+    }
+    RS_SYNC();
+    RS_LANE_LOOP(g, S::LT) {
+        const int a = c.agent_of_leg(g), dh = c.hipdof(g);
+        const float* W = H + AR::W0 + 12 * g; const float* St = H + AR::S0 + a * 42;
+        float dh_ = H[AR::Y0 + 2 * g], da_ = H[AR::Y0 + 2 * g + 1];
+        for (int k = 0; k < 6; k++) { const float dt = St[k * 7 + 6]; dh_ -= W[2 * k] * dt; da_ -= W[2 * k + 1] * dt; }
+        s.d[dh] = dh_; s.d[dh + 1] = da_;
+    }
     RS_SYNC();
 }
 
@@ -955,6 +1093,12 @@ RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
 #define RS_PHASE_SYNC()          // optional block-wide re-alignment between phases (instruction-cache locality)
 #define RS_BLOCK_ANY(p) (p)
 #endif
+#ifndef RS_ARROW
+#define RS_ARROW 1     // 0: always use the generic (block-diagonal / dense) assembly and elimination
+#endif
+#ifndef RS_ACC
+#define RS_ACC(i)
+#endif
 template <int LA, int LB>
 RS_HD void solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
@@ -965,21 +1109,26 @@ RS_HD void solve(Ctx<LA, LB>& c) {
     for (int iter = -1; iter < c.max_newton; iter++) {
         if (!RS_BLOCK_ANY(!conv)) break;
         const bool first = iter < 0;
+        RS_ACC(5);
         if (!conv && !first) {
             jt_forces(c);
             RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
             RS_SYNC();
         }
+        RS_ACC(0);
         RS_PHASE_SYNC();
-        if (!conv && !first) build_H(c);
+        if (!conv && !first) { if (RS_ARROW && s.coupled == 0) build_H_arrow(c); else build_H(c); }
+        RS_ACC(1);
         RS_PHASE_SYNC();
-        if (!conv && !first) chol_solve(c);                            // s.d = -H^-1 grad
+        if (!conv && !first) { if (RS_ARROW && s.coupled == 0) arrow_solve(c); else chol_solve(c); }      // s.d = -H^-1 grad
+        RS_ACC(2);
         RS_PHASE_SYNC();
         if (conv) continue;
         const float* vec = first ? s.x : s.d;
         twists(c, vec);
         rows_of(c, vec, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
         mat_vec(c, vec, first ? s.r : s.Md, first ? s.r : (const float*)0);     // first: r = M x0 - qfrc_smooth
+        RS_ACC(3);
         if (first) {
             RS_LANE_LOOP(k, s.ncon) {
                 // rows of the same geom pair at the previous evaluation's solution predict this evaluation's active rows
@@ -987,7 +1136,8 @@ RS_HD void solve(Ctx<LA, LB>& c) {
                 const int key = s.ckey(k);
                 for (int q = 0; q < s.nprev; q++) if ((s.cprev[q] >> 4) == key) bits = s.cprev[q] & 15;
                 int sign = 0;
-                for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
+                RS_UNROLL1
+            for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
                 s.set_cact(k, bits < 16 ? bits : sign);
             }
             RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
@@ -1045,18 +1195,24 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         RS_SYNC();
         RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.lmask, 1 << j); }     // sign set at the new point
         RS_SYNC();
+        RS_ACC(4);
         it++;
         if (same) conv = true;
     }
     RS_LANE_LOOP(k, s.ncon) { s.cprev[k] = (unsigned short)((s.ckey(k) << 4) | s.cact(k)); }
     if (RS_LANE0) s.nprev = s.ncon;
-    if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled; s.tot_ncon += s.ncon; if (it > s.max_iter) s.max_iter = it; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
+    if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled & 1; s.tot_ncon += s.ncon; if (it > s.max_iter) s.max_iter = it; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
     RS_SYNC();
 }
 
 // one forward evaluation: qacc(q, v) into s.x
 #ifndef RS_EVAL_SYNC
 #define RS_EVAL_SYNC()
+#endif
+#ifndef RS_CLOCK_BEGIN
+#define RS_CLOCK_BEGIN()      // developer instrumentation: busy cycles of a warp between the block-wide re-alignments
+#define RS_CLOCK_END()
+#define RS_CLOCK_MARK(i)
 #endif
 #ifndef RS_SUBSTEP_SYNC
 #define RS_SUBSTEP_SYNC()
@@ -1067,16 +1223,22 @@ RS_HD void solve(Ctx<LA, LB>& c) {
 template <int LA, int LB>
 RS_HD void forward(Ctx<LA, LB>& c) {
     RS_EVAL_SYNC();     // optional block-wide re-alignment of the warps (instruction-cache locality)
+    RS_CLOCK_BEGIN();
     fk(c);
     RS_PHASE_SYNC();
     dynamics(c);
     RS_PHASE_SYNC();
+    RS_CLOCK_MARK(0);
     collide(c);
+    RS_CLOCK_MARK(1);
     RS_PHASE_SYNC();
     make_constraints(c);
     RS_PHASE_SYNC();
     RS_SOLVE_SYNC();
+    RS_CLOCK_MARK(2);
     solve(c);
+    RS_CLOCK_MARK(3);
+    RS_CLOCK_END();
 }
 
 // mj_integratePos from q0 with velocity vel over dt into s.q
