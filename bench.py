@@ -108,6 +108,27 @@ def run_reference(args, rank, world):
             vals.append((rate, n, el))
     tot_n = sum(v[1] for v in vals); tot_t = sum(v[2] for v in vals)
     value = tot_n / tot_t
+    # the same CPU path driven the way the reference drives it: one spawned process per env, pickled pipe messages, Python env
+    # code around the physics call (subproc_vec_env.py:6-116, sumo.py / agents.py restated in oracle/env_oracle.py)
+    subproc = None
+    try:
+        import numpy as np
+        from oracle.subproc_oracle import SubprocOracleVecEnv
+        nw = min(cores, 16)
+        venv = SubprocOracleVecEnv('ant_ant', nw, seed=1)
+        venv.reset()
+        rng = np.random.RandomState(0)
+        for _ in range(5):
+            venv.step(rng.randn(nw, 2, 8))
+        n_sp, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 6.0:
+            venv.step(rng.randn(nw, 2, 8)); n_sp += nw
+        el = time.perf_counter() - t0
+        venv.close()
+        subproc = {'value': n_sp / el, 'unit': 'env-steps/s', 'workers': nw, 'envs': nw,
+                   'sample': '%d env-steps in %.1f s, one process per env pair, pickled pipes' % (n_sp, el)}
+    except Exception as ex:          # never let the secondary number take the reference arm down
+        subproc = {'unavailable': repr(ex)[:200]}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / len(vals), 'higher_is_better': True,
@@ -115,9 +136,10 @@ def run_reference(args, rank, world):
         'config': {'workload': 'RoboSumo-Ant-vs-Ant-v0 physics step, CPU oracle port on host cores',
                    'envs_per_step': envs, 'frame_skip': 5, 'integrator': 'RK4'},
         'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d env pairs x ~%.0f s per step, %d steps, N(0,1) actions' % (envs, per_step_s, args.steps)},
+                         'sample': '%d env pairs x ~%.1f s per step, %d steps, N(0,1) actions' % (envs, per_step_s, args.steps)},
         'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'subproc_protocol': subproc,
     }
     print(json.dumps(line), flush=True)
 
@@ -196,7 +218,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='env pairs per GPU')
-    ap.add_argument('--settle', type=int, default=40, help='untimed steps before warm-up so contacts exist')
+    ap.add_argument('--settle', type=int, default=300, help='untimed steps before warm-up: episode phases are mixed (steady state) after ~100 steps')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-flush', action='store_true')
     ap.add_argument('--no-learner', action='store_true', help='skip the rollout / PPO2-update secondary measurements')
@@ -280,7 +302,32 @@ def main():
     h2d = a32.nbytes
     d2h = henv.h_obs.nbytes + henv.h_rew.nbytes + henv.h_done.nbytes + henv.h_info.nbytes + henv.h_epi.nbytes
     learner = None
+    config4 = None
     if not args.no_learner:
+        # BASELINE.json configs[3]: 65 536 env pairs in total, sharded over the ranks (several waves of blocks per SM: the
+        # per-block slowest-warp tail of a single wave averages out)
+        del henv
+        E4 = 65536 // world
+        env4 = B200SumoVecEnv(ENV_ID, num_envs=E4, seed=777 + rank, device=local, device_api=True)
+        env4.reset()
+        pool4 = [torch.randn(E4, 2, 8, device=dev, generator=g) for _ in range(4)]
+        for t in range(60):
+            env4.step(pool4[t % 4])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for t in range(20):
+            env4.step(pool4[t % 4])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms4 = torch.tensor([e0.elapsed_time(e1) / 20], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        config4 = {'envs_total': E4 * world, 'envs_per_gpu': E4, 'ms_per_step': float(ms4.item()),
+                   'value': E4 * world / (float(ms4.item()) / 1e3), 'unit': 'env-steps/s', 'steps': 20}
+        env4.close(); del env4, pool4
         learner = measure_learner(args, E, local, rank, world, dev)
     if rank != 0:
         if world > 1:
@@ -322,6 +369,8 @@ def main():
     }
     if learner is not None:
         line['learner'] = learner
+    if config4 is not None:
+        line['config4_65536_pairs'] = config4
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

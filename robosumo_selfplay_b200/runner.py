@@ -128,8 +128,9 @@ class Runner:
         if self.device_env:
             flags = ep_done.cpu().numpy().astype(bool); info_h = ep_info.cpu().numpy()
             tt = round(time.time() - self.tstart, 6)
-            epinfos = [{'r': round(float(info_h[s, e, 0]), 6), 'dr': round(float(info_h[s, e, 1]), 6), 'l': int(info_h[s, e, 2]), 't': tt}
-                       for s, e in zip(*np.nonzero(flags))]
+            sel = info_h[flags].astype(np.float64)         # (step, env) order, as the reference appends them (runner.py:95-98)
+            epinfos = [{'r': r, 'dr': dr, 'l': l, 't': tt}
+                       for r, dr, l in zip(np.round(sel[:, 0], 6).tolist(), np.round(sel[:, 1], 6).tolist(), sel[:, 2].astype(np.int64).tolist())]
         else:
             epinfos = host_epinfos
         act_a = mb_actions.permute(2, 0, 1, 3)                      # [2][T][E][A]
