@@ -37,36 +37,65 @@ def read_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  Uses NVML in-process
+    (a sample every 20 ms; `nvidia-smi` takes longer to answer than a short timed region lasts) and falls back to the
+    `nvidia-smi --query-gpu` recipe when the NVML bindings are missing."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
         self.stop_flag = False
+        self.nvml = None
+        self.err = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception as ex:
+            self.nvml = None
+            self.err = repr(ex)[:160]
+
+    def _one_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((mhz, self.max_mhz, bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                             bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap)))
+
+    def _one_smi(self):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(',')]
+        if len(parts) >= 6:
+            self.samples.append((float(parts[0]), float(parts[1])) + tuple(p.lower().startswith('active') for p in parts[2:6]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(',')]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.1)
+                if self.nvml is not None:
+                    self._one_nvml()
+                else:
+                    self._one_smi()
+            except Exception as ex:
+                self.err = repr(ex)[:160]
+            time.sleep(0.02 if self.nvml is not None else 0.1)
 
     def summary(self):
         self.stop_flag = True
         if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(s[0]) for s in self.samples)
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'], 'error': self.err}
+        sm = sorted(s[0] for s in self.samples)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons, 'samples': len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons, 'samples': len(sm),
+                'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_port_rate(seconds, envs, threads):
