@@ -391,7 +391,7 @@ def main():
         'cpu_baseline': {'value': cpu_rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                          'sample': '%d env-steps (%d pairs, N(0,1) actions) in %.1f s on %d threads' % (cpu_n, 16 * cores, cpu_el, cores)},
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'steps': n_e2e, 'api': 'rs_step_host (B200SumoVecEnv host style: numpy actions in, obs/rew/done/info out)'},
+                'steps': n_e2e, 'api': 'rs_step_host (B200SumoVecEnv host style: numpy actions in through pinned staging, obs/rew/done/info/episode copied straight into the page-locked numpy result buffers)'},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'contact_full_envs': ncon_note,

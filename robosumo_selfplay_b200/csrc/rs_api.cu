@@ -346,7 +346,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     CUDA_OK(cudaMalloc(&h->d_am, 2 * sizeof(rs_agent_model)));
     CUDA_OK(cudaMemcpy(h->d_am, agents, 2 * sizeof(rs_agent_model), cudaMemcpyHostToDevice));
     EnvDev& d = h->d;
-    d.E = E; d.am = h->d_am; d.h = cfg->timestep; d.max_newton = cfg->newton_iters > 0 ? cfg->newton_iters : 8;
+    d.E = E; d.am = h->d_am; d.h = cfg->timestep; d.max_newton = cfg->newton_iters > 0 ? cfg->newton_iters : 16;
     d.P.frame_skip = cfg->frame_skip; d.P.timestep_limit = cfg->timestep_limit; d.P.ring_limit = cfg->ring_limit;
     d.P.init_pos_noise = cfg->init_pos_noise; d.P.init_vel_noise = cfg->init_vel_noise;
     d.P.seed_lo = (uint32_t)cfg->seed; d.P.seed_hi = (uint32_t)(cfg->seed >> 32);
@@ -443,23 +443,37 @@ int rs_step(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* do
     });
 }
 
+// true when `p` is page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory): the copy engine can use it directly
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* done, float* info, float* episode,
                  int auto_reset) {
     if (!h || !actions || !obs || !rew || !done) return fail(RS_ERR_ARG, "rs_step_host: bad argument%s", "");
     const int E = h->d.E, OD = h->obsA + h->obsB;
-    memcpy(h->h_act, actions, sizeof(float) * E * h->nu);
-    CUDA_OK(cudaMemcpyAsync(h->s_act, h->h_act, sizeof(float) * E * h->nu, cudaMemcpyHostToDevice, h->stream));
+    // caller buffers that are page-locked are used as they are; pageable ones go through the handle's pinned staging
+    const float* a_src = actions;
+    if (!is_pinned(actions)) { memcpy(h->h_act, actions, sizeof(float) * E * h->nu); a_src = h->h_act; }
+    CUDA_OK(cudaMemcpyAsync(h->s_act, a_src, sizeof(float) * E * h->nu, cudaMemcpyHostToDevice, h->stream));
     int rc = rs_step(h, h->s_act, h->s_obs, h->s_rew, h->s_done, h->s_info, h->s_epi, auto_reset, h->stream);
     if (rc) return rc;
-    CUDA_OK(cudaMemcpyAsync(h->h_obs, h->s_obs, sizeof(float) * E * OD, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(cudaMemcpyAsync(h->h_rew, h->s_rew, sizeof(float) * E * 2, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(cudaMemcpyAsync(h->h_done, h->s_done, E * 2, cudaMemcpyDeviceToHost, h->stream));
-    if (info) CUDA_OK(cudaMemcpyAsync(h->h_info, h->s_info, sizeof(float) * E * 2 * RS_INFO_DIM, cudaMemcpyDeviceToHost, h->stream));
-    if (episode) CUDA_OK(cudaMemcpyAsync(h->h_epi, h->s_epi, sizeof(float) * E * 3, cudaMemcpyDeviceToHost, h->stream));
+    struct Out { void* user; void* stage; const void* dev; size_t bytes; bool direct; };
+    Out outs[5] = {
+        { obs, h->h_obs, h->s_obs, sizeof(float) * E * OD, false },
+        { rew, h->h_rew, h->s_rew, sizeof(float) * E * 2, false },
+        { done, h->h_done, h->s_done, (size_t)E * 2, false },
+        { info, h->h_info, h->s_info, sizeof(float) * E * 2 * RS_INFO_DIM, false },
+        { episode, h->h_epi, h->s_epi, sizeof(float) * E * 3, false } };
+    for (Out& o : outs) {
+        if (!o.user) continue;
+        o.direct = is_pinned(o.user);
+        CUDA_OK(cudaMemcpyAsync(o.direct ? o.user : o.stage, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_OK(cudaStreamSynchronize(h->stream));
-    memcpy(obs, h->h_obs, sizeof(float) * E * OD); memcpy(rew, h->h_rew, sizeof(float) * E * 2); memcpy(done, h->h_done, E * 2);
-    if (info) memcpy(info, h->h_info, sizeof(float) * E * 2 * RS_INFO_DIM);
-    if (episode) memcpy(episode, h->h_epi, sizeof(float) * E * 3);
+    for (Out& o : outs) if (o.user && !o.direct) memcpy(o.user, o.stage, o.bytes);
     return RS_OK;
 }
 

@@ -115,7 +115,7 @@ class _AgentView:
 
 class B200SumoVecEnv(VecEnv):
     def __init__(self, env_id='RoboSumo-Ant-vs-Ant-v0', num_envs=8, seed=42, device=0, adjust_z=0.0,
-                 device_api=False, auto_reset=True, newton_iters=8, timestep_limit=TIMESTEP_LIMIT):
+                 device_api=False, auto_reset=True, newton_iters=16, timestep_limit=TIMESTEP_LIMIT):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -153,11 +153,18 @@ class B200SumoVecEnv(VecEnv):
         self.d_done = torch.zeros((E, 2), dtype=torch.uint8, device=dev)
         self.d_info = torch.zeros((E, 2, 8), dtype=torch.float32, device=dev)
         self.d_epi = torch.zeros((E, 3), dtype=torch.float32, device=dev)
-        self.h_obs = np.zeros((E, oa + ob) if self.mixed else (E, 2, oa), dtype=np.float32)
-        self.h_rew = np.zeros((E, 2), dtype=np.float32)
-        self.h_done = np.zeros((E, 2), dtype=np.uint8)
-        self.h_info = np.zeros((E, 2, 8), dtype=np.float32)
-        self.h_epi = np.zeros((E, 3), dtype=np.float32)
+        # host-style result buffers are page-locked, so rs_step_host copies device -> caller memory with no staging hop
+        def pinned(shape, dtype):
+            tt = torch.zeros(shape, dtype=dtype, pin_memory=True)
+            self._pinned.append(tt)               # keeps the allocation alive behind the numpy view
+            return tt.numpy()
+        self._pinned = []
+        self.h_obs = pinned((E, oa + ob) if self.mixed else (E, 2, oa), torch.float32)
+        self.h_rew = pinned((E, 2), torch.float32)
+        self.h_done = pinned((E, 2), torch.uint8)
+        self.h_info = pinned((E, 2, 8), torch.float32)
+        self.h_epi = pinned((E, 3), torch.float32)
+        self.h_act = pinned((E, self.nu), torch.float32)
         self.waiting = False
         self.closed = False
         self._pending = None
@@ -215,7 +222,8 @@ class B200SumoVecEnv(VecEnv):
                                        ctypes.c_void_p(self.d_info.data_ptr()), ctypes.c_void_p(self.d_epi.data_ptr()),
                                        1 if self.auto_reset else 0, self._stream()))
             return self._obs_out(self.d_obs), self.d_rew, self.d_done, (self.d_info, self.d_epi)
-        a = np.ascontiguousarray(np.asarray(self._flat_actions(actions), dtype=np.float32).reshape(self.num_envs, self.nu))
+        self.h_act[...] = np.asarray(self._flat_actions(actions), dtype=np.float32).reshape(self.num_envs, self.nu)
+        a = self.h_act
         self.torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self._L.rs_step_host(self._h, self._np(a), self._np(self.h_obs), self._np(self.h_rew),
                                         self._np(self.h_done), self._np(self.h_info), self._np(self.h_epi),
