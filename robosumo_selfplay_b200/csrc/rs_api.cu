@@ -100,6 +100,7 @@ static int fail(int code, const char* fmt, const char* detail) {
 struct EnvDev {
     int E;
     float *qpos, *qvel, *warm, *ep_ret, *ep_dret;
+    int* pred;                         // active-set prediction carried across steps: [E][4 + MAXC/2] = limit masks (non-zero, negative side, loaded), nprev, cprev pairs
     int *ep_step, *status, *diag;      // diag[E][4]: Newton iterations, coupled evaluations, contacts summed over the last env step, max iterations of one evaluation
     unsigned int* ep_count;
     const rs_agent_model* am;
@@ -143,7 +144,21 @@ __device__ __forceinline__ void load_state(Ctx<LA, LB>& c, const EnvDev& d, int 
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NQ) { s.q[i] = d.qpos[(size_t)e * S::NQ + i]; }
     RS_LANE_LOOP(i, S::NV) { s.v[i] = d.qvel[(size_t)e * S::NV + i]; s.x[i] = d.warm[(size_t)e * S::NV + i]; }
-    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; s.max_iter = 0; s.nprev = 0; }
+    // active sets at the end of the previous step (limit rows as three bit masks, contact rows by key): the first evaluation of
+    // this step predicts from them exactly as later evaluations predict from their predecessor
+    const int* pr = d.pred + (size_t)e * (4 + S::MAXC / 2);
+    const int nz = pr[0], neg = pr[1], loaded = pr[2];
+    RS_LANE_LOOP(j, S::NU) { s.lsgn[j] = ((nz >> j) & 1) ? (((neg >> j) & 1) ? -1.f : 1.f) : 0.f; s.ljar[j] = ((loaded >> j) & 1) ? -1.f : 1.f; }
+    RS_LANE_LOOP(k, S::MAXC / 2) { const int w = pr[4 + k]; s.cprev[2 * k] = (unsigned short)(w & 0xFFFF); s.cprev[2 * k + 1] = (unsigned short)((unsigned)w >> 16); }
+    if (RS_LANE0) { s.status = d.status[e]; s.ncon = 0; s.niter = 0; s.tot_iter = 0; s.tot_coupled = 0; s.tot_ncon = 0; s.max_iter = 0; s.nprev = pr[3]; }
+    RS_SYNC();
+}
+template <int LA, int LB>
+__device__ __forceinline__ void clear_prediction(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(j, S::NU) { s.lsgn[j] = 0.f; s.ljar[j] = 1.f; }
+    if (RS_LANE0) s.nprev = 0;
     RS_SYNC();
 }
 template <int LA, int LB>
@@ -152,6 +167,13 @@ __device__ __forceinline__ void store_state(Ctx<LA, LB>& c, const EnvDev& d, int
     S& s = *c.s;
     RS_LANE_LOOP(i, S::NQ) { d.qpos[(size_t)e * S::NQ + i] = s.q[i]; }
     RS_LANE_LOOP(i, S::NV) { d.qvel[(size_t)e * S::NV + i] = s.v[i]; d.warm[(size_t)e * S::NV + i] = s.x[i]; }
+    static_assert(S::NU <= 32, "limit masks are one word");
+    const int lane = threadIdx.x & 31;
+    const float sg = lane < S::NU ? s.lsgn[lane] : 0.f, jr = lane < S::NU ? s.ljar[lane] : 1.f;
+    const unsigned nz = __ballot_sync(0xffffffffu, sg != 0.f), neg = __ballot_sync(0xffffffffu, sg < 0.f), loaded = __ballot_sync(0xffffffffu, jr < 0.f);
+    int* pr = d.pred + (size_t)e * (4 + S::MAXC / 2);
+    if (lane == 0) { pr[0] = (int)nz; pr[1] = (int)neg; pr[2] = (int)loaded; pr[3] = s.nprev; }
+    RS_LANE_LOOP(k, S::MAXC / 2) { pr[4 + k] = (int)((unsigned)s.cprev[2 * k] | ((unsigned)s.cprev[2 * k + 1] << 16)); }
 }
 template <int LA, int LB>
 __device__ __forceinline__ void set_act(Ctx<LA, LB>& c, const float* ctrl) {
@@ -179,6 +201,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_reset(EnvDev d, const uint8_t* 
     S& s = *c.s;
     unsigned int ep = d.ep_count[e] + 1;
     env_reset_state(c, d.P, (uint32_t)e, ep);
+    clear_prediction(c);
     store_state(c, d, e);
     if (RS_LANE0) { d.ep_count[e] = ep; d.ep_step[e] = 0; d.ep_ret[e] = 0.f; d.ep_dret[e] = 0.f; d.status[e] = 0; }
     const int OD = (7 + 2*LA) + (6 + 2*LA) + 6 * (1 + 3*LA) + 14 + (7 + 2*LB) + (6 + 2*LB) + 6 * (1 + 3*LB) + 14;
@@ -206,6 +229,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_set_state(EnvDev d, const float
         qq[3] *= inv; qq[4] *= inv; qq[5] *= inv; qq[6] *= inv;
     }
     RS_SYNC();
+    clear_prediction(c);
     store_state(c, d, e);
     if (RS_LANE0) d.status[e] = 0;
     const int OD = (7 + 2*LA) + (6 + 2*LA) + 6 * (1 + 3*LA) + 14 + (7 + 2*LB) + (6 + 2*LB) + 6 * (1 + 3*LB) + 14;
@@ -269,6 +293,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     if (o.done[0] && auto_reset) {
         unsigned int ep = d.ep_count[e] + 1;
         env_reset_state(c, d.P, (uint32_t)e, ep);
+        clear_prediction(c);
         store_state(c, d, e);
         if (lane == 0) { d.ep_count[e] = ep; d.ep_step[e] = 0; d.ep_ret[e] = 0.f; d.ep_dret[e] = 0.f; d.status[e] = st & RS_STATUS_CONTACT_FULL; }
         env_write_obs(c, obs + (size_t)e * OD, -1.f);
@@ -351,6 +376,8 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     d.P.init_pos_noise = cfg->init_pos_noise; d.P.init_vel_noise = cfg->init_vel_noise;
     d.P.seed_lo = (uint32_t)cfg->seed; d.P.seed_hi = (uint32_t)(cfg->seed >> 32);
     CUDA_OK(cudaMalloc(&d.qpos, sizeof(float) * E * h->nq)); CUDA_OK(cudaMalloc(&d.qvel, sizeof(float) * E * h->nv));
+    const size_t pred_bytes = sizeof(int) * (size_t)E * (4 + (h->LA + h->LB <= 8 ? 24 : 32) / 2);
+    CUDA_OK(cudaMalloc(&d.pred, pred_bytes)); CUDA_OK(cudaMemset(d.pred, 0, pred_bytes));
     CUDA_OK(cudaMalloc(&d.warm, sizeof(float) * E * h->nv)); CUDA_OK(cudaMalloc(&d.ep_ret, sizeof(float) * E));
     CUDA_OK(cudaMalloc(&d.ep_dret, sizeof(float) * E)); CUDA_OK(cudaMalloc(&d.ep_step, sizeof(int) * E));
     CUDA_OK(cudaMalloc(&d.status, sizeof(int) * E)); CUDA_OK(cudaMalloc(&d.ep_count, sizeof(unsigned int) * E));
@@ -383,7 +410,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
 
 void rs_destroy(rs_env* h) {
     if (!h) return;
-    cudaFree(h->d_am); cudaFree(h->d.qpos); cudaFree(h->d.qvel); cudaFree(h->d.warm); cudaFree(h->d.ep_ret);
+    cudaFree(h->d_am); cudaFree(h->d.qpos); cudaFree(h->d.qvel); cudaFree(h->d.warm); cudaFree(h->d.pred); cudaFree(h->d.ep_ret);
     cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.diag); cudaFree(h->d.status); cudaFree(h->d.ep_count);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_epi); cudaFreeHost(h->h_done);
     cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_epi); cudaFree(h->s_done);

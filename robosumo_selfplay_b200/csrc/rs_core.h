@@ -584,6 +584,27 @@ RS_HD void collide(Ctx<LA, LB>& c) {
     RS_SYNC();
     if (s.ncon > S::MAXC) { if (RS_LANE0) { s.ncon = S::MAXC; s.status |= RS_STATUS_CONTACT_FULL; } }
     RS_SYNC();
+    // the atomic counter hands out slots in arrival order; sort the list by key (rank = number of smaller keys, staged through
+    // the H array) so that every later sum over contacts runs in a fixed order and a step is bit-reproducible
+    if (s.ncon > 1) {
+        static_assert(12 * S::MAXC <= S::HDED, "contact staging must fit in the H array");
+        RS_LANE_LOOP(k, s.ncon) {
+            const int key = s.ckey(k);
+            int rank = 0;
+            RS_UNROLL1
+            for (int j = 0; j < s.ncon; j++) rank += s.ckey(j) < key ? 1 : 0;
+            float* G = s.H + 12 * rank;
+            st3(G, ld3(s.cpos[k])); st3(G + 3, ld3(s.cn[k])); st3(G + 6, ld3(s.ct1[k]));
+            G[9] = s.cD[k]; G[10] = s.caref[k][0]; ((int*)G)[11] = s.cbody[k];
+        }
+        RS_SYNC();
+        RS_LANE_LOOP(k, s.ncon) {
+            const float* G = s.H + 12 * k;
+            st3(s.cpos[k], ld3(G)); st3(s.cn[k], ld3(G + 3)); st3(s.ct1[k], ld3(G + 6));
+            s.cD[k] = G[9]; s.caref[k][0] = G[10]; s.cbody[k] = ((const int*)G)[11];
+        }
+        RS_SYNC();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
