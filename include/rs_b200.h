@@ -129,6 +129,10 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
                 float* log_ratio, int precision, void* stream);
 int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
                  float lr, long long step_t, float beta1, float beta2, float eps, double* scratch, float* gnorm_out, void* stream);
+/* the five scalars PPOModel.train returns (model.py:137, loss_names): stats5 = [pg_loss, vf_loss, entropy, approxkl, clipfrac] as
+ * doubles, from the (all-reduced) stat sums behind the gradient in grad_stats and the logstd of `params`; call it BEFORE
+ * rs_adam_step: the reference evaluates the entropy with the pre-update parameters (same session.run as the train op) */
+int rs_ppo_stats(const float* grad_stats, const float* params, int obs_dim, int act_dim, long long global_n, double* stats5, void* stream);
 
 /* tcgen05 self-test (debug hook): D[128,64] = op(A)*op(B) with kind::tf32; prm13 = {a_rows,a_cols,b_rows,b_cols,a_mn,b_mn,
  * a_lbo,a_sbo,a_step,b_lbo,b_sbo,b_step,nk} (bytes), host pointer */

@@ -670,6 +670,14 @@ int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, in
     return RS_OK;
 }
 
+int rs_ppo_stats(const float* grad_stats, const float* params, int obs_dim, int act_dim, long long global_n, double* stats5, void* stream) {
+    if (!grad_stats || !params || !stats5 || global_n < 1) return fail(RS_ERR_ARG, "rs_ppo_stats: bad argument%s", "");
+    const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
+    rsl::k_ppo_stats<<<1, 32, 0, (cudaStream_t)stream>>>(grad_stats, params, L.P, L.logstd, act_dim, 1.0 / (double)global_n, stats5);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
 
 /* tcgen05 descriptor/layout self-test: D[128,64] = op(A) * op(B) through kind::tf32 UMMA (see rs_tc.cuh) */
 int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, void* stream) {

@@ -509,4 +509,16 @@ __global__ void k_adam(float* __restrict__ params, float* __restrict__ m, float*
     params[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// [pg_loss, vf_loss, entropy, approxkl, clipfrac] (model.py:137): means of the four stat sums stored behind the gradient, and the
+// DiagGaussian entropy sum(logstd + 0.5 log(2 pi e)) (distributions.py:244-245) of the parameters as they are now
+__global__ void k_ppo_stats(const float* __restrict__ grad_stats, const float* __restrict__ params, int P, int logstd_off, int A,
+                            double inv_n, double* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        double ent = 0;
+        for (int i = 0; i < A; i++) ent += (double)params[logstd_off + i] + 1.4189385332046727;      // 0.5 * log(2 pi e)
+        out[0] = (double)grad_stats[P] * inv_n; out[1] = (double)grad_stats[P + 1] * inv_n; out[2] = ent;
+        out[3] = (double)grad_stats[P + 2] * inv_n; out[4] = (double)grad_stats[P + 3] * inv_n;
+    }
+}
+
 }  // namespace rsl

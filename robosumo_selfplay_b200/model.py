@@ -83,19 +83,18 @@ class PPOModel:
         if self.comm is not None:
             self.comm.all_reduce_sum(self.adv_sums)
         log_ratio = t.empty(n, dtype=t.float32, device=self.device) if want_log_ratio else None
-        entropy = (self.act_model.logstd().double() + 0.5 * np.log(2.0 * np.pi * np.e)).sum()      # before the update (model.py:70)
         _lib.check(L.rs_ppo_grad(self._p(self.params), self.D, self.A, self._p(obs), self._p(actions), self._p(returns), self._p(values),
                                  self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(self.adv_sums), float(cliprange),
                                  self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio),
                                  1 if self.precision == 'tf32' else 0, st))
         if self.comm is not None:
             self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums]: one latency-bound NCCL all-reduce
+        stats = t.empty(5, dtype=t.float64, device=self.device)         # loss_names order; entropy with the pre-update logstd (model.py:70)
+        _lib.check(L.rs_ppo_stats(self._p(self.grad_stats), self._p(self.params), self.D, self.A, gn, self._p(stats), st))
         self.t += 1
         mgn = float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0
         _lib.check(L.rs_adam_step(self._p(self.params), self._p(self.m), self._p(self.v), self._p(self.grad_stats), self.D, self.A,
                                   self.ent_coef, mgn, float(lr), self.t, 0.9, 0.999, 1e-5, self._p(self.scratch), self._p(self.gnorm), st))
-        s4 = self.grad_stats[self.P:self.P + 4].double() / float(gn)
-        stats = t.stack([s4[0], s4[1], entropy, s4[2], s4[3]])           # device tensor in loss_names order
         return stats, log_ratio
 
     def stats_to_list(self, stats_dev):
