@@ -366,6 +366,14 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     h->wpb = (int)((227 * 1024 - 2 * sizeof(rs_agent_model)) / sb);
     if (h->wpb > RS_WPB) h->wpb = RS_WPB;
     if (h->wpb < 1) { delete h; return fail(RS_ERR_UNSUPPORTED, "slab does not fit in shared memory%s", ""); }
+    {   // fewer pairs than one wave can hold: spread them over all SMs (fewer warps per block = less issue contention) instead
+        // of filling some SMs and leaving others idle.  (With two or more waves an even split measured slower: the block
+        // scheduler backfills finished SMs anyway.)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        const long long E = cfg->num_envs;
+        if (E <= (long long)sms * h->wpb) { const int even = (int)((E + sms - 1) / sms); if (even >= 1 && even < h->wpb) h->wpb = even; }
+    }
     h->smem = sb * h->wpb;
     const int E = cfg->num_envs;
     CUDA_OK(cudaMalloc(&h->d_am, 2 * sizeof(rs_agent_model)));
