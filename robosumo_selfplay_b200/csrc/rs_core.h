@@ -1158,7 +1158,7 @@ RS_HD void solve(Ctx<LA, LB>& c) {
                 for (int q = 0; q < s.nprev; q++) if ((s.cprev[q] >> 4) == key) bits = s.cprev[q] & 15;
                 int sign = 0;
                 RS_UNROLL1
-            for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
+                for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
                 s.set_cact(k, bits < 16 ? bits : sign);
             }
             RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
