@@ -181,7 +181,7 @@ def measure_learner(args, E, local, rank, world, dev):
     from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
     from robosumo_selfplay_b200.model import PPOModel
     from robosumo_selfplay_b200.runner import Runner
-    from robosumo_selfplay_b200.dist import Comm, split_minibatch
+    from robosumo_selfplay_b200.dist import Comm, split_minibatch, legacy_shuffle
     from robosumo_selfplay_b200 import _lib
     T, nmb, nep = args.nsteps, 32, 6
     comm = Comm() if world > 1 else None
@@ -209,7 +209,7 @@ def measure_learner(args, E, local, rank, world, dev):
     def one_update():
         inds = np.arange(N)
         for ep in range(nep):
-            np.random.shuffle(inds)
+            legacy_shuffle(inds)
             if world == 1:
                 di = torch.as_tensor(inds.astype(np.int32), device=dev)
                 parts = [di[s0:s0 + nbt] for s0 in range(0, N, nbt)]
@@ -237,7 +237,7 @@ def measure_learner(args, E, local, rank, world, dev):
             'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
                            'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_s / 1e12,
                            'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,
-                           'note': 'wall clock incl. host-side NumPy shuffles (bit-exact schedule) and the gradient all-reduce when N > 1'}}
+                           'note': 'wall clock incl. the host-side replay of the legacy NumPy shuffles (bit-exact schedule) and the gradient all-reduce when N > 1'}}
 
 
 def main():

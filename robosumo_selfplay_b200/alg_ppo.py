@@ -19,7 +19,7 @@ import numpy as np
 
 from .model import PPOModel
 from .runner import Runner
-from .dist import split_minibatch
+from .dist import split_minibatch, legacy_shuffle
 
 
 def constfn(val):
@@ -191,7 +191,7 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
         stat_acc = []
         early_stop = False
         for epoch in range(noptepochs):
-            np.random.shuffle(inds)                   # legacy global RandomState: same stream as the reference
+            legacy_shuffle(inds)                      # np.random.shuffle(inds) on the legacy global RandomState, replayed bit-exactly (dist.py)
             starts = list(range(0, update_sample_num, nbatch_train))
             if world == 1:
                 dev_inds = torch.as_tensor(inds.astype(np.int32), device=device)

@@ -687,6 +687,44 @@ int rs_ppo_stats(const float* grad_stats, const float* params, int obs_dim, int 
     return RS_OK;
 }
 
+// ---- legacy NumPy shuffle replay (host) -----------------------------------------------------------------------------------
+static inline void mt19937_refill(uint32_t* mt) {
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, A = 0x9908b0dfu;
+    int kk;
+    for (kk = 0; kk < 624 - 397; kk++) { uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+    for (; kk < 623; kk++) { uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+    uint32_t y = (mt[623] & UPPER) | (mt[0] & LOWER);
+    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+}
+static inline uint32_t mt19937_next(uint32_t* mt, int* pos) {
+    if (*pos >= 624) { mt19937_refill(mt); *pos = 0; }
+    uint32_t y = mt[(*pos)++];
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+    return y;
+}
+int rs_legacy_shuffle(uint32_t* key, int* pos, int64_t* x, long long n) {
+    if (!key || !pos || !x || n < 0 || *pos < 0 || *pos > 624) return fail(RS_ERR_ARG, "rs_legacy_shuffle: bad argument%s", "");
+    if (n > 0x100000000LL) return fail(RS_ERR_UNSUPPORTED, "rs_legacy_shuffle: n beyond the 32-bit interval path%s", "");
+    // the swap partners depend on the generator only, not on the data: draw them a block ahead and prefetch, so that the random
+    // accesses into x (4-64 MB) overlap instead of paying one cache miss per element
+    const int B = 64;
+    long long jj[B];
+    for (long long i = n - 1; i >= 1; i -= B) {
+        const int m = (int)(i >= B ? B : i);                 // partners for i, i-1, ..., i-m+1
+        for (int q = 0; q < m; q++) {
+            const uint64_t top = (uint64_t)(i - q);
+            uint64_t mask = top;
+            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+            uint64_t j;
+            do { j = (uint64_t)mt19937_next(key, pos) & mask; } while (j > top);
+            jj[q] = (long long)j;
+            __builtin_prefetch(x + j, 1, 0);
+        }
+        for (int q = 0; q < m; q++) { const long long a = i - q, b = jj[q]; const int64_t tmp = x[a]; x[a] = x[b]; x[b] = tmp; }
+    }
+    return RS_OK;
+}
+
 /* tcgen05 descriptor/layout self-test: D[128,64] = op(A) * op(B) through kind::tf32 UMMA (see rs_tc.cuh) */
 int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, void* stream) {
     if (!prm13 || !A || !B || !D) return fail(RS_ERR_ARG, "rs_tc_selftest: bad argument%s", "");

