@@ -181,7 +181,7 @@ def measure_learner(args, E, local, rank, world, dev):
     from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
     from robosumo_selfplay_b200.model import PPOModel
     from robosumo_selfplay_b200.runner import Runner
-    from robosumo_selfplay_b200.dist import Comm, split_minibatch, legacy_shuffle
+    from robosumo_selfplay_b200.dist import Comm, split_minibatch, EpochPermutations
     from robosumo_selfplay_b200 import _lib
     T, nmb, nep = args.nsteps, 32, 6
     comm = Comm() if world > 1 else None
@@ -194,22 +194,23 @@ def measure_learner(args, E, local, rank, world, dev):
     runner.nsteps = 8
     runner.run(1, as_numpy=False)                       # warm-up
     runner.nsteps = T
-    torch.cuda.synchronize()
-    l0 = _lib.lib().rs_launch_count()
-    t0 = time.perf_counter()
-    R = runner.run(1, as_numpy=False)
-    torch.cuda.synchronize()
-    roll_s = time.perf_counter() - t0
-    roll_launches = _lib.lib().rs_launch_count() - l0
+    roll_times = []
+    for rep in range(3):                               # median of three rollouts (a single one occasionally catches a host hiccup)
+        torch.cuda.synchronize()
+        l0 = _lib.lib().rs_launch_count()
+        t0 = time.perf_counter()
+        R = runner.run(1, as_numpy=False)
+        torch.cuda.synchronize()
+        roll_times.append(time.perf_counter() - t0)
+        roll_launches = _lib.lib().rs_launch_count() - l0
+    roll_s = sorted(roll_times)[1]
     data = {k: R[k][0].contiguous() for k in ('obs', 'returns', 'actions', 'values', 'neglogpacs')}
     N_local, N = E * T, E * T * world
     nbt = N // nmb
     lo, hi = rank * N_local, (rank + 1) * N_local
     model = models[0]
     def one_update():
-        inds = np.arange(N)
-        for ep in range(nep):
-            legacy_shuffle(inds)
+        for inds in EpochPermutations(N, nep):       # the reference's per-epoch np.random.shuffle, replayed bit-exactly one epoch ahead
             if world == 1:
                 di = torch.as_tensor(inds.astype(np.int32), device=dev)
                 parts = [di[s0:s0 + nbt] for s0 in range(0, N, nbt)]
@@ -233,7 +234,7 @@ def measure_learner(args, E, local, rank, world, dev):
     roll_s, upd_s = float(tt[0]), float(tt[1])
     flops = 114.6e3 * N * nep
     return {'rollout': {'value': E * world * T / roll_s, 'unit': 'env-steps/s', 'T': T, 'launches_per_step': roll_launches / T,
-                        'note': 'Runner.run: 1 fused MLP launch (4 policy evaluations, tcgen05 tf32) + 1 sampling launch + 1 physics launch per step, no host sync'},
+                        'rollout_seconds': roll_times, 'note': 'Runner.run: 1 fused MLP launch (4 policy evaluations, tcgen05 tf32) + 1 sampling launch + 1 physics launch per step, no host sync; median of 3 rollouts'},
             'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
                            'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_s / 1e12,
                            'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,

@@ -142,6 +142,15 @@ int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, v
  * the 20 forward evaluations of the step, and the largest iteration count of a single evaluation (cf. mjData.solver_iter / ncon) */
 int rs_get_diag(rs_env* h, int* diag, void* stream);
 
+/* single-GPU convenience: rs_adv_moments -> rs_ppo_grad -> rs_ppo_stats -> rs_adam_step in ONE call (one host->library transition
+ * per minibatch instead of four; a data-parallel caller uses the pieces and all-reduces between them).  beta1 = 0.9, beta2 = 0.999,
+ * eps = 1e-5 as model.py:121; adv_sums [2], scratch [1] doubles and grad_stats [P + 8] floats are caller-owned device buffers. */
+int rs_ppo_minibatch_step(float* params, float* m, float* v, int obs_dim, int act_dim, const float* obs, const float* actions,
+                          const float* returns, const float* values, const float* old_nlp, const float* weights, const int* idx, int n,
+                          float cliprange, float ent_coef, float vf_coef, float max_grad_norm, float lr, long long step_t,
+                          float* workspace, float* grad_stats, double* adv_sums, double* scratch, float* gnorm_out, double* stats5,
+                          float* log_ratio, int precision, void* stream);
+
 /* HOST function (no GPU): the reference's per-epoch minibatch permutation, `np.random.shuffle(inds)` on the legacy global
  * RandomState (alg_ppo.py:364), replayed bit-exactly (swap partners drawn a block ahead and prefetched: on par with NumPy at 0.5 M indices, 2.3x faster at 8 M).  `key` [624] and
  * `*pos` are the MT19937 state as returned by np.random.get_state() and are advanced in place; `x` [n] is permuted in place.

@@ -19,7 +19,7 @@ import numpy as np
 
 from .model import PPOModel
 from .runner import Runner
-from .dist import split_minibatch, legacy_shuffle
+from .dist import split_minibatch, EpochPermutations
 
 
 def constfn(val):
@@ -187,11 +187,11 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
         update_sample_num = n_local * world if weights is None else n_local
 
         # ---- epochs x minibatches (alg_ppo.py:355-398) ----
-        inds = np.arange(update_sample_num)
+        perms = EpochPermutations(update_sample_num, noptepochs)     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
         stat_acc = []
         early_stop = False
         for epoch in range(noptepochs):
-            legacy_shuffle(inds)                      # np.random.shuffle(inds) on the legacy global RandomState, replayed bit-exactly (dist.py)
+            inds = next(perms)
             starts = list(range(0, update_sample_num, nbatch_train))
             if world == 1:
                 dev_inds = torch.as_tensor(inds.astype(np.int32), device=device)
@@ -210,6 +210,7 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
                     break
             if early_stop:
                 break
+        perms.close()
         lossvals = torch.stack(stat_acc).double().mean(0).cpu().numpy().tolist()          # np.mean(mblossvals, axis=0)
         tnow = time.perf_counter()
         history.append(dict(update=update, opponent=idx, rollout_s=t_roll - tstart, update_s=tnow - t_roll, losses=lossvals))

@@ -687,6 +687,20 @@ int rs_ppo_stats(const float* grad_stats, const float* params, int obs_dim, int 
     return RS_OK;
 }
 
+int rs_ppo_minibatch_step(float* params, float* m, float* v, int obs_dim, int act_dim, const float* obs, const float* actions,
+                          const float* returns, const float* values, const float* old_nlp, const float* weights, const int* idx, int n,
+                          float cliprange, float ent_coef, float vf_coef, float max_grad_norm, float lr, long long step_t,
+                          float* workspace, float* grad_stats, double* adv_sums, double* scratch, float* gnorm_out, double* stats5,
+                          float* log_ratio, int precision, void* stream) {
+    int rc = rs_adv_moments(idx, n, returns, values, adv_sums, stream);
+    if (rc) return rc;
+    rc = rs_ppo_grad(params, obs_dim, act_dim, obs, actions, returns, values, old_nlp, weights, idx, n, n, adv_sums, cliprange, ent_coef,
+                     vf_coef, workspace, grad_stats, log_ratio, precision, stream);
+    if (rc) return rc;
+    if (stats5) { rc = rs_ppo_stats(grad_stats, params, obs_dim, act_dim, n, stats5, stream); if (rc) return rc; }
+    return rs_adam_step(params, m, v, grad_stats, obs_dim, act_dim, ent_coef, max_grad_norm, lr, step_t, 0.9f, 0.999f, 1e-5f, scratch, gnorm_out, stream);
+}
+
 // ---- legacy NumPy shuffle replay (host) -----------------------------------------------------------------------------------
 static inline void mt19937_refill(uint32_t* mt) {
     const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, A = 0x9908b0dfu;

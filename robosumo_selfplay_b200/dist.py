@@ -70,3 +70,59 @@ def legacy_shuffle(inds):
                                             ctypes.c_longlong(inds.shape[0])))
     np.random.set_state((name, key, p.value, has_gauss, cached))
     return inds
+
+
+class EpochPermutations:
+    """The `noptepochs` successive `np.random.shuffle(inds)` permutations of one update (alg_ppo.py:357-364), computed one epoch
+    AHEAD on a helper thread while the caller enqueues the minibatches of the current epoch (the host shuffle of 0.5-8 M
+    indices is longer than the GPU work of an epoch).  The helper works on a private copy of the legacy MT19937 state; the
+    global `np.random` state is advanced only when a permutation is handed out, so an early stop (kl_threshold) leaves the
+    stream exactly where the reference would: nothing speculative is ever committed."""
+
+    def __init__(self, n, nepochs):
+        import numpy as np
+        from concurrent.futures import ThreadPoolExecutor
+        name, key, pos, self._hg, self._cg = np.random.get_state()
+        assert name == 'MT19937'
+        self._key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        self._pos = int(pos)
+        self._inds = np.arange(n)
+        self._left = int(nepochs)
+        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._fut = None
+        self._launch()
+
+    def _compute(self):
+        import ctypes
+        from . import _lib
+        p = ctypes.c_int(self._pos)
+        _lib.check(_lib.lib().rs_legacy_shuffle(ctypes.c_void_p(self._key.ctypes.data), ctypes.byref(p),
+                                                ctypes.c_void_p(self._inds.ctypes.data), ctypes.c_longlong(self._inds.shape[0])))
+        self._pos = p.value
+        return self._inds.copy(), self._key.copy(), self._pos
+
+    def _launch(self):
+        if self._left > 0:
+            self._left -= 1
+            self._fut = self._pool.submit(self._compute)
+        else:
+            self._fut = None
+            self._pool.shutdown(wait=False)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        import numpy as np
+        if self._fut is None:
+            raise StopIteration
+        perm, key, pos = self._fut.result()
+        np.random.set_state(('MT19937', key, pos, self._hg, self._cg))
+        self._launch()
+        return perm
+
+    def close(self):
+        if self._fut is not None:
+            self._fut.result()
+            self._fut = None
+            self._pool.shutdown(wait=False)

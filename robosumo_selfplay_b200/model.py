@@ -79,6 +79,18 @@ class PPOModel:
         gn = int(global_n) if global_n is not None else n
         st = self._stream()
         L = self._L
+        if self.comm is None and gn == n:          # single GPU: the whole minibatch step is one library call
+            log_ratio = t.empty(n, dtype=t.float32, device=self.device) if want_log_ratio else None
+            stats = t.empty(5, dtype=t.float64, device=self.device)
+            self.t += 1
+            mgn = float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0
+            _lib.check(L.rs_ppo_minibatch_step(self._p(self.params), self._p(self.m), self._p(self.v), self.D, self.A, self._p(obs),
+                                               self._p(actions), self._p(returns), self._p(values), self._p(neglogpacs), self._p(weights),
+                                               self._p(idx), n, float(cliprange), self.ent_coef, self.vf_coef, mgn, float(lr), self.t,
+                                               self._p(self._workspace(n)), self._p(self.grad_stats), self._p(self.adv_sums),
+                                               self._p(self.scratch), self._p(self.gnorm), self._p(stats), self._p(log_ratio),
+                                               1 if self.precision == 'tf32' else 0, st))
+            return stats, log_ratio
         _lib.check(L.rs_adv_moments(self._p(idx), n, self._p(returns), self._p(values), self._p(self.adv_sums), st))
         if self.comm is not None:
             self.comm.all_reduce_sum(self.adv_sums)

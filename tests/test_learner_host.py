@@ -134,3 +134,27 @@ def test_legacy_shuffle_replay_is_bit_exact():
         tail = np.random.randint(0, 1 << 30, 5), np.random.normal(0, 1, 3)
         assert (a == b).all()
         assert (tail_ref[0] == tail[0]).all() and (tail_ref[1] == tail[1]).all()
+
+
+def test_epoch_permutations_commit_only_what_is_consumed():
+    """EpochPermutations hands out the same permutations as successive np.random.shuffle calls and leaves the global stream
+    where the reference would be, also when the epochs stop early."""
+    from robosumo_selfplay_b200.dist import EpochPermutations
+    n = 50000
+    np.random.seed(11)
+    a = np.arange(n); ref = []
+    for _ in range(3):
+        np.random.shuffle(a); ref.append(a.copy())
+    after3 = np.random.randint(0, 1 << 30, 4)
+    np.random.seed(11)
+    got = list(EpochPermutations(n, 3))
+    assert len(got) == 3 and all((g == r).all() for g, r in zip(got, ref))
+    assert (np.random.randint(0, 1 << 30, 4) == after3).all()
+    # early stop after 2 of 6 epochs: the stream continues as if only 2 shuffles had been drawn
+    np.random.seed(11)
+    b = np.arange(n); np.random.shuffle(b); np.random.shuffle(b)
+    after2 = np.random.randint(0, 1 << 30, 4)
+    np.random.seed(11)
+    it = EpochPermutations(n, 6)
+    next(it); p2 = next(it); it.close()
+    assert (p2 == b).all() and (np.random.randint(0, 1 << 30, 4) == after2).all()
