@@ -51,7 +51,9 @@ if __name__ == '__main__':
         m = PPOModel(ob_dim=D, ac_dim=A, device=comm.local_rank, comm=comm, precision=precision)
         lo, hi = comm.shard(N)
         p_multi = train(m, dd, lo, hi, comm, precision)
-        out[precision] = dict(max_abs_diff=float(np.abs(p_single - p_multi).max()), moved=float(np.abs(p_single - init).max()))
+        d = np.abs(p_single - p_multi)
+        out[precision] = dict(max_abs_diff=float(d.max()), moved=float(np.abs(p_single - init).max()), worst_index=int(d.argmax()),
+                              n_above_1e_6=int((d > 1e-6).sum()), median_abs_diff=float(np.median(d)), n_params=int(d.size))
     if comm.rank == 0:
         print(json.dumps(dict(world=comm.world, **out)))
     comm.barrier()
