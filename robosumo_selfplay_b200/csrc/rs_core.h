@@ -1120,6 +1120,9 @@ RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
 #ifndef RS_ACC
 #define RS_ACC(i)
 #endif
+#ifndef RS_SOLVE_TRACE
+#define RS_SOLVE_TRACE(s, it)     // host-emulation analysis hook (tools), empty in every build of the product
+#endif
 template <int LA, int LB>
 RS_HD void solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
@@ -1220,6 +1223,7 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         it++;
         if (same) conv = true;
     }
+    RS_SOLVE_TRACE(s, it);
     RS_LANE_LOOP(k, s.ncon) { s.cprev[k] = (unsigned short)((s.ckey(k) << 4) | s.cact(k)); }
     if (RS_LANE0) s.nprev = s.ncon;
     if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled & 1; s.tot_ncon += s.ncon; if (it > s.max_iter) s.max_iter = it; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
