@@ -77,6 +77,80 @@ class KVLogger:
         self.kvs = {}
 
 
+class EpisodeMonitor:
+    """`monitor.csv` (baselines/bench/monitor.py:95-121): a JSON header line, then one `r,l,t` row per finished episode.  The
+    reference wraps every env process in its own Monitor and writes one file per env; the vectorised env writes ONE file for all
+    E pairs, rows in (step, env) order of completion."""
+
+    def __init__(self, log_dir, env_id):
+        import json
+        self.f = None
+        if log_dir:
+            os.makedirs(log_dir, exist_ok=True)
+            self.f = open(osp.join(log_dir, 'monitor.csv'), 'wt')
+            self.f.write('# %s \n' % json.dumps({'t_start': time.time(), 'env_id': env_id}))
+            self.f.write('r,l,t\n')
+            self.f.flush()
+
+    def write(self, epinfos):
+        if self.f is not None and epinfos:
+            self.f.write(''.join('%s,%s,%s\n' % (e['r'], e['l'], e['t']) for e in epinfos))
+            self.f.flush()
+
+    def close(self):
+        if self.f is not None:
+            self.f.close()
+            self.f = None
+
+
+def ratio_figure(log_dir, update, idx, raw, nlp, clip_ratio, neglogp_threshold):
+    """The per-update IS-ratio diagnostics of alg_ppo.py:292-318: five 100-bin histograms (log off-policy / off-env / total ratio
+    clipped below at -100, both agents' neglogp clipped to +-threshold) computed ON THE DEVICE and saved as fig/ratio_<update>.npz;
+    the same five panels are also rendered to fig/ratio_<update>.png when matplotlib is importable (it is not in this image)."""
+    import torch
+    out = {}
+    for name, x in (('off_policy', raw[0]), ('off_env', raw[1]), ('total', raw[2])):
+        lx = torch.clamp(torch.log(x.double()), min=-100.0)
+        lo, hi = float(lx.min()), float(lx.max())
+        hi = hi if hi > lo else lo + 1.0
+        out[name + '_log_hist'] = torch.histc(lx, bins=100, min=lo, max=hi).cpu().numpy()
+        out[name + '_log_range'] = np.array([lo, hi])
+        out[name + '_clip_frac'] = np.array(float((x > clip_ratio).double().mean()))
+    for a in range(2):
+        v = torch.clamp(nlp[a].double().flatten(), -neglogp_threshold, neglogp_threshold)
+        lo, hi = float(v.min()), float(v.max())
+        hi = hi if hi > lo else lo + 1.0
+        out['neglogp%d_hist' % a] = torch.histc(v, bins=100, min=lo, max=hi).cpu().numpy()
+        out['neglogp%d_range' % a] = np.array([lo, hi])
+    out['opponent_version'] = np.array(idx)
+    fig_dir = osp.join(log_dir, 'fig')
+    os.makedirs(fig_dir, exist_ok=True)
+    np.savez(osp.join(fig_dir, 'ratio_%d.npz' % update), **out)
+    try:
+        import matplotlib
+        matplotlib.use('Agg')
+        import matplotlib.pyplot as plt
+    except Exception:
+        return out
+    plt.figure(figsize=(16, 9))
+    panels = [((2, 3, 1), 'off_policy', 'off-policy ratio (log scale): %.2f%% clipped'), ((2, 3, 2), 'off_env', 'off-env ratio (log scale): %.2f%% clipped'),
+              ((2, 3, 3), 'total', 'off-policy-env ratio (log scale): %.2f%% clipped')]
+    for pos, name, title in panels:
+        plt.subplot(*pos)
+        edges = np.linspace(out[name + '_log_range'][0], out[name + '_log_range'][1], 101)
+        plt.bar(edges[:-1], out[name + '_log_hist'], width=edges[1] - edges[0], align='edge')
+        plt.title(title % (100.0 * float(out[name + '_clip_frac'])))
+    for a, pos in ((0, (2, 2, 3)), (1, (2, 2, 4))):
+        plt.subplot(*pos)
+        edges = np.linspace(out['neglogp%d_range' % a][0], out['neglogp%d_range' % a][1], 101)
+        plt.bar(edges[:-1], out['neglogp%d_hist' % a], width=edges[1] - edges[0], align='edge')
+        plt.title('-log pi_1(a^%d|o^%d)' % (a + 1, a + 1))
+    plt.suptitle('opponent version: %d' % idx)
+    plt.savefig(osp.join(fig_dir, 'ratio_%d.png' % update))
+    plt.close()
+    return out
+
+
 def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_opponent_data=None, seed=None, nsteps=2048, ent_coef=0.0,
           lr=3e-4, vf_coef=0.5, max_grad_norm=0.5, gamma=0.99, lam=0.95, rho_bar=1., c_bar=1., log_interval=10, nminibatches=4,
           noptepochs=4, cliprange=0.2, save_interval=1, load_path=None, nagent=2, anneal_bound=500, vgap=None, kl_threshold=None,
@@ -123,6 +197,10 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
     epinfobuf = deque(maxlen=100)
     tfirststart = time.perf_counter()
     version_gap, history = [], []
+    # observability: monitor.csv, fig/ratio_<update>.npz(+png), ratio_summary.pkl -- rank 0 only
+    monitor = EpisodeMonitor(log_dir if rank == 0 else None, getattr(env, 'env_id', 'RoboSumo'))
+    ratio_log = dict(off_policy_ratio_mean=[], off_policy_ratio_clip_frac=[], off_env_ratio_mean=[], off_env_ratio_clip_frac=[],
+                     total_ratio_mean=[], total_ratio_clip_frac=[], ppo_clip_frac=[], approxkl=[])
     lo, hi = rank * nbatch_local, (rank + 1) * nbatch_local
     prev = None
 
@@ -166,7 +244,15 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
         prev = R
         t_roll = time.perf_counter()
         epinfobuf.extend(R['epinfos'])
+        monitor.write(R['epinfos'])
         clip_ratio = rho_bar
+        raw3 = [torch.nan_to_num(R[k], nan=clip_ratio) for k in ('off_policy_ratio', 'off_env_ratio', 'ratio')]      # alg_ppo.py:258-279
+        rstat = torch.stack([torch.stack([x.double().mean(), (x > clip_ratio).double().mean()]) for x in raw3]).cpu().numpy()
+        for (mk, ck), (mean_, frac_) in zip((('off_policy_ratio_mean', 'off_policy_ratio_clip_frac'), ('off_env_ratio_mean', 'off_env_ratio_clip_frac'),
+                                             ('total_ratio_mean', 'total_ratio_clip_frac')), rstat):
+            ratio_log[mk].append(float(mean_)); ratio_log[ck].append(float(frac_))
+        if rank == 0 and log_dir:
+            ratio_figure(log_dir, update, idx, raw3, R['neglogpacs'], clip_ratio, neglogp_threshold)
         fix = lambda x: torch.clamp(torch.nan_to_num(x, nan=clip_ratio), 0.0, clip_ratio)      # alg_ppo.py:258-279
         off_policy_ratio, total_ratio = fix(R['off_policy_ratio']), fix(R['ratio'])
         usable = (R['neglogpacs'][1] < neglogp_threshold).nonzero().flatten()
@@ -212,6 +298,13 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
                 break
         perms.close()
         lossvals = torch.stack(stat_acc).double().mean(0).cpu().numpy().tolist()          # np.mean(mblossvals, axis=0)
+        ratio_log['approxkl'].append(float(lossvals[3])); ratio_log['ppo_clip_frac'].append(float(lossvals[4]))
+        if rank == 0 and log_dir and opponent_mode == 'random' and (update % 100 == 0 or update == 1):
+            import pickle
+            with open(osp.join(log_dir, 'ratio_summary.pkl'), 'wb') as f:      # same nine lists, same order (incl. the repeated
+                pickle.dump([version_gap, ratio_log['off_policy_ratio_mean'], ratio_log['off_env_ratio_clip_frac'],      # clip-frac entry) as alg_ppo.py:468-472
+                             ratio_log['off_env_ratio_mean'], ratio_log['off_env_ratio_clip_frac'], ratio_log['total_ratio_mean'],
+                             ratio_log['total_ratio_clip_frac'][-1] if ratio_log['total_ratio_clip_frac'] else 0.0, ratio_log['ppo_clip_frac'], ratio_log['approxkl']], f)
         tnow = time.perf_counter()
         history.append(dict(update=update, opponent=idx, rollout_s=t_roll - tstart, update_s=tnow - t_roll, losses=lossvals))
         if update_fn is not None:
@@ -234,5 +327,7 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
             logger.dumpkvs()
         if save_interval and (update % save_interval == 0 or update == 1):
             save(update)
+    monitor.close()
     model.history = history
+    model.ratio_log = ratio_log
     return model

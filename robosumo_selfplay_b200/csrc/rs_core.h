@@ -898,7 +898,7 @@ template <int LA, int LB>
 struct Arrow {
     typedef Slab<LA, LB> S;
     enum { A0 = 0, B0 = 72, D0 = 72 + 12 * S::LT, NCOPY = 72 + 15 * S::LT, W0 = NCOPY, Y0 = W0 + 12 * S::LT, S0 = Y0 + 2 * S::LT, END = S0 + 84 };
-    static_assert(END <= S::HDED, "compact arrowhead H must fit in the H array");
+    static_assert((int)END <= (int)S::HDED, "compact arrowhead H must fit in the H array");
     static_assert(offsetof(S, Ml) - offsetof(S, Mr) == (72 + 12 * S::LT) * sizeof(float), "Mr | Mc | Ml must be contiguous");
 };
 

@@ -133,7 +133,7 @@ def test_reference_train_signature_and_checkpoint_roundtrip(tmp_path):
     assert np.array_equal(m2.get_flat(), m.get_flat())
 
 
-def test_runner_and_learn_end_to_end_small():
+def test_runner_and_learn_end_to_end_small(tmp_path):
     """Runner.run on the device env: outputs are self-consistent with the policies; learn() runs 2 updates and its
     minibatch schedule equals the NumPy legacy-RandomState replay of the reference's call order."""
     import torch
@@ -168,7 +168,7 @@ def test_runner_and_learn_end_to_end_small():
     try:
         env = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E, seed=7, device_api=True)
         model = alg_ppo.learn(env=env, total_timesteps=2 * E * T, seed=11, nsteps=T, nminibatches=4, noptepochs=2, lr=1e-3, gamma=0.995, lam=1.0,
-                              rho_bar=10., c_bar=1., log_interval=1, anneal_bound=1000, opponent_mode='random')
+                              rho_bar=10., c_bar=1., log_interval=1, anneal_bound=1000, opponent_mode='random', log_dir=str(tmp_path))
     finally:
         PPOModel.train_indexed = orig
     opp, sched = po.minibatch_schedule(11, D, A, 2, E * T, 4, 2, 'random')
@@ -178,6 +178,24 @@ def test_runner_and_learn_end_to_end_small():
         assert np.array_equal(a_, b_)                                      # bit-exact permutation
     assert [h['opponent'] for h in model.history] == opp
     assert np.isfinite(model.get_flat()).all()
+    # observability files: progress.csv keys, monitor.csv rows, per-update ratio histograms, ratio_summary.pkl
+    import json, pickle
+    prog = open(tmp_path / 'progress.csv').read().splitlines()
+    for key in ('misc/serial_timesteps', 'misc/nupdates', 'misc/total_timesteps', 'misc/explained_variance', 'eprewmean', 'epdenserewmean',
+                'eplenmean', 'misc/time_elapsed', 'loss/policy_loss', 'loss/value_loss', 'loss/policy_entropy', 'loss/approxkl', 'loss/clipfrac'):
+        assert key in prog[0].split(','), key
+    assert len(prog) == 3
+    mon = open(tmp_path / 'monitor.csv').read().splitlines()
+    assert mon[0].startswith('#') and json.loads(mon[0][1:])['env_id'] == 'RoboSumo-Ant-vs-Ant-v0' and mon[1] == 'r,l,t'
+    for row in mon[2:]:
+        r_, l_, t_ = row.split(','); float(r_); assert int(l_) >= 1; float(t_)
+    z = np.load(tmp_path / 'fig' / 'ratio_2.npz')
+    for name in ('off_policy', 'off_env', 'total'):
+        assert z[name + '_log_hist'].shape == (100,) and z[name + '_log_hist'].sum() == E * T and 0.0 <= float(z[name + '_clip_frac']) <= 1.0
+    assert z['neglogp0_hist'].sum() == E * T and int(z['opponent_version']) == opp[1]
+    summ = pickle.load(open(tmp_path / 'ratio_summary.pkl', 'rb'))
+    assert len(summ) == 9 and summ[0] == [0]                               # written at update 1: version gap list so far
+    assert len(model.ratio_log['approxkl']) == 2
 
 
 @pytest.mark.parametrize('Dw,Aw', [(165, 12), (209, 16)])
