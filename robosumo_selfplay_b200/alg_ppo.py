@@ -239,6 +239,9 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
         if comm is not None:
             comm.broadcast(models[1].params, 0)       # opponent-snapshot broadcast over NCCL (98 KB)
 
+        # the update's permutations depend on the generator stream only: when the sample count is known up front they are all
+        # computed on a helper thread WHILE the rollout runs (nothing else draws from np.random until they are consumed)
+        perms = EpochPermutations(nbatch, noptepochs, ahead=noptepochs) if use_opponent_data is None else None
         # ---- rollout (device resident) ----
         R = runner.run(update, as_numpy=False)
         prev = R
@@ -273,7 +276,9 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
         update_sample_num = n_local * world if weights is None else n_local
 
         # ---- epochs x minibatches (alg_ppo.py:355-398) ----
-        perms = EpochPermutations(update_sample_num, noptepochs)     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
+        if perms is None:
+            perms = EpochPermutations(update_sample_num, noptepochs)     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
+        assert perms._inds.shape[0] == update_sample_num
         stat_acc = []
         early_stop = False
         for epoch in range(noptepochs):

@@ -73,14 +73,16 @@ def legacy_shuffle(inds):
 
 
 class EpochPermutations:
-    """The `noptepochs` successive `np.random.shuffle(inds)` permutations of one update (alg_ppo.py:357-364), computed one epoch
-    AHEAD on a helper thread while the caller enqueues the minibatches of the current epoch (the host shuffle of 0.5-8 M
-    indices is longer than the GPU work of an epoch).  The helper works on a private copy of the legacy MT19937 state; the
-    global `np.random` state is advanced only when a permutation is handed out, so an early stop (kl_threshold) leaves the
-    stream exactly where the reference would: nothing speculative is ever committed."""
+    """The `noptepochs` successive `np.random.shuffle(inds)` permutations of one update (alg_ppo.py:357-364), computed AHEAD on a
+    helper thread: one epoch ahead by default, so that the host shuffle of 0.5-8 M indices overlaps the GPU work of the current
+    epoch, or all of them (`ahead=nepochs`) when the caller creates the object before the rollout.  The helper works on a
+    private copy of the legacy MT19937 state; the global `np.random` state is advanced only when a permutation is handed out,
+    so an early stop (kl_threshold) leaves the stream exactly where the reference would: nothing speculative is committed.
+    Nobody else may draw from `np.random` between construction and the last `next()` (the rollout and the update do not)."""
 
-    def __init__(self, n, nepochs):
+    def __init__(self, n, nepochs, ahead=1):
         import numpy as np
+        from collections import deque
         from concurrent.futures import ThreadPoolExecutor
         name, key, pos, self._hg, self._cg = np.random.get_state()
         assert name == 'MT19937'
@@ -88,9 +90,10 @@ class EpochPermutations:
         self._pos = int(pos)
         self._inds = np.arange(n)
         self._left = int(nepochs)
-        self._pool = ThreadPoolExecutor(max_workers=1)
-        self._fut = None
-        self._launch()
+        self._pool = ThreadPoolExecutor(max_workers=1)       # one worker: the shuffles continue one generator stream, in order
+        self._queue = deque()
+        for _ in range(max(1, int(ahead))):
+            self._launch()
 
     def _compute(self):
         import ctypes
@@ -104,25 +107,23 @@ class EpochPermutations:
     def _launch(self):
         if self._left > 0:
             self._left -= 1
-            self._fut = self._pool.submit(self._compute)
-        else:
-            self._fut = None
-            self._pool.shutdown(wait=False)
+            self._queue.append(self._pool.submit(self._compute))
 
     def __iter__(self):
         return self
 
     def __next__(self):
         import numpy as np
-        if self._fut is None:
+        if not self._queue:
+            self._pool.shutdown(wait=False)
             raise StopIteration
-        perm, key, pos = self._fut.result()
+        perm, key, pos = self._queue.popleft().result()
         np.random.set_state(('MT19937', key, pos, self._hg, self._cg))
         self._launch()
         return perm
 
     def close(self):
-        if self._fut is not None:
-            self._fut.result()
-            self._fut = None
-            self._pool.shutdown(wait=False)
+        self._left = 0
+        while self._queue:
+            self._queue.popleft().result()
+        self._pool.shutdown(wait=False)
