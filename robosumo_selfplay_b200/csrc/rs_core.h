@@ -1135,6 +1135,16 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         const bool first = iter < 0;
         RS_ACC(5);
         if (!conv && !first) {
+            // coupling that matters for THIS iteration's H: only contacts with active rows contribute J^T D J, so an inter- or
+            // intra-agent contact that is inside the margin but not loaded does not force the dense paths
+            if (RS_LANE0) s.coupled = 0;
+            RS_SYNC();
+            RS_LANE_LOOP(k, s.ncon) {
+                const int bA = s.bA(k), bB = s.bB(k);
+                if (bA >= 0 && s.cact(k) != 0)
+                    RS_ATOMIC_OR(&s.coupled, ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1 : 2);
+            }
+            RS_SYNC();
             jt_forces(c);
             RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
             RS_SYNC();
