@@ -209,8 +209,8 @@ def measure_learner(args, E, local, rank, world, dev):
     nbt = N // nmb
     lo, hi = rank * N_local, (rank + 1) * N_local
     model = models[0]
-    def one_update():
-        for inds in EpochPermutations(N, nep):       # the reference's per-epoch np.random.shuffle, replayed bit-exactly one epoch ahead
+    def one_update(perms=None):
+        for inds in (perms if perms is not None else EpochPermutations(N, nep)):     # the reference's per-epoch np.random.shuffle, replayed bit-exactly one epoch ahead
             if world == 1:
                 di = torch.as_tensor(inds.astype(np.int32), device=dev)
                 parts = [di[s0:s0 + nbt] for s0 in range(0, N, nbt)]
@@ -228,17 +228,29 @@ def measure_learner(args, E, local, rank, world, dev):
     one_update()
     torch.cuda.synchronize()
     upd_s = time.perf_counter() - t0
-    tt = torch.tensor([roll_s, upd_s], dtype=torch.float64, device=dev)
+    # the same update the way alg_ppo.learn runs it: the six permutations depend on the generator stream only and are drawn on the
+    # helper thread WHILE the rollout runs, so inside the training loop the update does not wait for them
+    perms = EpochPermutations(N, nep, ahead=nep)
+    runner.run(1, as_numpy=False)
+    torch.cuda.synchronize()
+    if comm is not None:
+        comm.barrier()
+    t0 = time.perf_counter()
+    one_update(perms)
+    torch.cuda.synchronize()
+    upd_loop_s = time.perf_counter() - t0
+    tt = torch.tensor([roll_s, upd_s, upd_loop_s], dtype=torch.float64, device=dev)
     if comm is not None:
         comm.all_reduce_sum(tt); tt /= world
-    roll_s, upd_s = float(tt[0]), float(tt[1])
+    roll_s, upd_s, upd_loop_s = float(tt[0]), float(tt[1]), float(tt[2])
     flops = 114.6e3 * N * nep
     return {'rollout': {'value': E * world * T / roll_s, 'unit': 'env-steps/s', 'T': T, 'launches_per_step': roll_launches / T,
                         'rollout_seconds': roll_times, 'note': 'Runner.run: 1 fused MLP launch (4 policy evaluations, tcgen05 tf32) + 1 sampling launch + 1 physics launch per step, no host sync; median of 3 rollouts'},
             'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
                            'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_s / 1e12,
                            'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,
-                           'note': 'wall clock incl. the host-side replay of the legacy NumPy shuffles (bit-exact schedule) and the gradient all-reduce when N > 1'}}
+                           'in_training_loop': {'value': upd_loop_s, 'unit': 's/iter', 'note': 'permutations drawn by the helper thread during the preceding rollout, as alg_ppo.learn does'},
+                           'note': 'stand-alone update: wall clock incl. the host-side replay of the six legacy NumPy shuffles (bit-exact schedule; one epoch ahead of the GPU) and the gradient all-reduce when N > 1'}}
 
 
 def main():

@@ -551,7 +551,7 @@ static int mlp_forward_jobs(const rsl::MlpJobs& J, int njobs, int obs_dim, int a
         size_t sm = rsl::tc_tile_bytes(obs_dim);
         static std::atomic<size_t> cur(0);
         if (sm > cur.load()) { CUDA_OK(cudaFuncSetAttribute(rsl::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cur.store(sm); }
-        rsl::k_mlp_forward_tc<<<grid, RSL_TILE, sm, (cudaStream_t)stream>>>(J, obs_dim, act_dim, n);
+        rsl::k_mlp_forward_tc<<<grid, RSL_TC_THREADS, sm, (cudaStream_t)stream>>>(J, obs_dim, act_dim, n);
     } else {
         size_t sm = rsl::tile_bytes(obs_dim, act_dim);
         if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_mlp_forward: obs_dim too large for one tile%s", "");
@@ -656,7 +656,7 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
     a.old_nlp = old_nlp; a.weights = weights; a.idx = idx; a.n = n; a.adv_sums = adv_sums; a.adv_count = (double)global_n;
     a.cliprange = cliprange; a.ent_coef = ent_coef; a.vf_coef = vf_coef; a.inv_n = 1.0f / (float)global_n;
     a.gpart = workspace; a.spart = workspace + (size_t)nb * L.P; a.log_ratio = log_ratio;
-    if (precision == 1) rsl::k_ppo_tile_tc<<<nb, RSL_TILE, sm, st>>>(a);
+    if (precision == 1) rsl::k_ppo_tile_tc<<<nb, RSL_TC_THREADS, sm, st>>>(a);
     else rsl::k_ppo_tile<<<nb, RSL_TILE, sm, st>>>(a);
     rsl::k_grad_reduce<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, grad_stats + L.P);
     g_launches += 2;

@@ -109,6 +109,10 @@ __device__ inline void tc_stage_x(const TcTile& t, const float* __restrict__ X, 
         }
     }
 }
+// The tensor-core kernels run RSL_TC_THREADS = 256 threads on a 128-row tile: thread t works on row t % 128 and on the column
+// half t / 128 (accumulator columns 32 ch .. 32 ch + 31) -- eight warps instead of four to hide the shared-memory, TMEM and
+// L2 latencies of the epilogues, transposes and staging loops; scalar per-row work (loss, outputs) is done by the ch == 0 threads.
+#define RSL_TC_THREADS 256
 struct TcCtx { uint32_t tmem; uint64_t* bar; uint32_t phase; };
 
 // D[tmem] = A[128 x K] * B^T with B given as [64 x K] tile (both K-major); called by all threads, issued by thread 0
@@ -127,17 +131,14 @@ __device__ __forceinline__ void tc_gemm(TcCtx& c, const float* A, const float* B
 }
 // epilogue of F1 / F2: row r = threadIdx.x of the accumulator -> relu(acc + bias) into an operand tile [128][64]
 __device__ __forceinline__ void tc_relu_to_tile(const TcCtx& c, const float* bias, float* tile) {
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127, c0 = (threadIdx.x >> 7) * 32;
     float o[32];
+    rstc::tmem_ld32(c.tmem, c0, o);
 #pragma unroll
-    for (int c0 = 0; c0 < RSL_H; c0 += 32) {
-        rstc::tmem_ld32(c.tmem, c0, o);
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-            float4 v = make_float4(fmaxf(o[q] + bias[c0 + q], 0.f), fmaxf(o[q + 1] + bias[c0 + q + 1], 0.f),
-                                   fmaxf(o[q + 2] + bias[c0 + q + 2], 0.f), fmaxf(o[q + 3] + bias[c0 + q + 3], 0.f));
-            *reinterpret_cast<float4*>(tile + tile_off(r, c0 + q, RSL_H)) = v;
-        }
+    for (int q = 0; q < 32; q += 4) {
+        float4 v = make_float4(fmaxf(o[q] + bias[c0 + q], 0.f), fmaxf(o[q + 1] + bias[c0 + q + 1], 0.f),
+                               fmaxf(o[q + 2] + bias[c0 + q + 2], 0.f), fmaxf(o[q + 3] + bias[c0 + q + 3], 0.f));
+        *reinterpret_cast<float4*>(tile + tile_off(r, c0 + q, RSL_H)) = v;
     }
 }
 // forward of the staged net: H1, H2 tiles filled; head outputs of this thread's row in out8
@@ -146,17 +147,28 @@ __device__ __forceinline__ void tc_net_forward(TcCtx& c, const TcTile& t, float*
     tc_relu_to_tile(c, t.b0, t.h1);
     tc_gemm(c, t.h1, t.w1t, RSL_H);
     tc_relu_to_tile(c, t.b1, t.h2);
-    const int r = threadIdx.x;
+    // heads: each thread sums its own column half of H2 (its own writes: no barrier needed); ch == 1 hands its partial to ch == 0
+    const int r = threadIdx.x & 127, ch = threadIdx.x >> 7;
 #pragma unroll
-    for (int q = 0; q < RSL_HW; q++) outh[q] = t.bh[q];
-    for (int k = 0; k < RSL_H; k += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(t.h2 + tile_off(r, k, RSL_H));      // own writes: no barrier needed
+    for (int q = 0; q < RSL_HW; q++) outh[q] = ch ? 0.f : t.bh[q];
+    for (int k = 32 * ch; k < 32 * ch + 32; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(t.h2 + tile_off(r, k, RSL_H));
         const float av[4] = { a.x, a.y, a.z, a.w };
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
             for (int q = 0; q < RSL_HW; q++) outh[q] = fmaf(av[u], t.wh[(k + u) * RSL_HW + q], outh[q]);
     }
+    if (ch) {
+#pragma unroll
+        for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = outh[q];
+    }
+    __syncthreads();
+    if (!ch) {
+#pragma unroll
+        for (int q = 0; q < RSL_HW; q++) outh[q] += t.dout[r * RSL_DS + q];
+    }
+    __syncthreads();                                    // dout is reused by the caller
 }
 __device__ __forceinline__ void tc_begin(TcCtx& c, uint64_t* bar, uint32_t* slot) {
     if (threadIdx.x == 0) rstc::mbar_init(bar, 1);
@@ -173,7 +185,7 @@ __device__ __forceinline__ void tc_end(TcCtx& c) {
 }
 
 // ---- inference (same job contract as k_mlp_forward) ----
-__global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(MlpJobs J, int D, int A, int n) {
+__global__ void __launch_bounds__(RSL_TC_THREADS) k_mlp_forward_tc(MlpJobs J, int D, int A, int n) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
@@ -185,20 +197,21 @@ __global__ void __launch_bounds__(RSL_TILE) k_mlp_forward_tc(MlpJobs J, int D, i
     const float* __restrict__ params = J.params[job];
     float* __restrict__ mean = J.mean[job];
     float* __restrict__ value = J.value[job];
-    const int row0 = blockIdx.x * RSL_TILE, g = row0 + threadIdx.x;
+    const int row0 = blockIdx.x * RSL_TILE, g = row0 + (threadIdx.x & 127);
+    const bool writer = threadIdx.x < 128 && g < n;
     tc_stage_x(t, J.X[job], J.ldx[job], nullptr, row0, n, D);
     float o[RSL_HW];
     if (mean) {
         tc_stage_net(t, params, D, L.pi_w0, L.pi_b0, L.pi_w1, L.pi_b1, L.pi_w, L.pi_b, A);
         tc_net_forward(c, t, o);
-        if (g < n) for (int q = 0; q < A; q++) mean[(size_t)g * A + q] = o[q];
+        if (writer) for (int q = 0; q < A; q++) mean[(size_t)g * A + q] = o[q];
         rstc::tc_fence_before();
         __syncthreads();
     }
     if (value) {
         tc_stage_net(t, params, D, L.vf_w0, L.vf_b0, L.vf_w1, L.vf_b1, L.vf_w, L.vf_b, 1);
         tc_net_forward(c, t, o);
-        if (g < n) value[g] = o[0];
+        if (writer) value[g] = o[0];
     }
     tc_end(c);
 }
@@ -256,55 +269,53 @@ __device__ inline void tc_wgrad(TcCtx& c, const TcTile& t, const float* __restri
                                 const float* __restrict__ dz, float* __restrict__ gw, float* __restrict__ gb) {
     float* inT = t.w0t;
     float* dzT = t.w0t + 128 * 64;
-    const int sl = threadIdx.x & 63, fh = threadIdx.x >> 6;
+    // transposing copies: a warp moves an 8-feature x 4-sample patch per instruction, lane = 4 * (feature % 8) + (sample % 4), so that
+    // the 32 destination words are consecutive (conflict-free stores; the loads are 2-way conflicted at worst)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int fi = lane >> 2, si = lane & 3;
     for (int half = 0; half < 2; half++) {
-        const int smp = half * 64 + sl;
-        for (int f = fh * (nf >> 1); f < (fh + 1) * (nf >> 1); f += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(in + tile_off(smp, f, Cin));
-            inT[tile_off(f, sl, 64)] = f == ones_row ? 1.f : v.x; inT[tile_off(f + 1, sl, 64)] = f + 1 == ones_row ? 1.f : v.y;
-            inT[tile_off(f + 2, sl, 64)] = f + 2 == ones_row ? 1.f : v.z; inT[tile_off(f + 3, sl, 64)] = f + 3 == ones_row ? 1.f : v.w;
+        for (int p = warp; p < (nf >> 3) * 16; p += nw) {           // patches: feature group fg (8 features) x sample group sg (4 samples)
+            const int fg = p >> 4, sg = p & 15, f = fg * 8 + fi;
+            const float v = in[tile_off(half * 64 + sg * 4 + si, f, Cin)];
+            inT[fg * 512 + sg * 32 + lane] = f == ones_row ? 1.f : v;
         }
-        if (ones_row >= nf && fh == 0) inT[tile_off(ones_row, sl, 64)] = 1.f;
-        for (int j = fh * 32; j < fh * 32 + 32; j += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(dz + tile_off(smp, j, RSL_H));
-            dzT[tile_off(j, sl, 64)] = v.x; dzT[tile_off(j + 1, sl, 64)] = v.y; dzT[tile_off(j + 2, sl, 64)] = v.z; dzT[tile_off(j + 3, sl, 64)] = v.w;
+        if (ones_row >= nf) { for (int sl = threadIdx.x; sl < 64; sl += blockDim.x) inT[tile_off(ones_row, sl, 64)] = 1.f; }
+        for (int p = warp; p < (RSL_H >> 3) * 16; p += nw) {
+            const int fg = p >> 4, sg = p & 15;
+            dzT[fg * 512 + sg * 32 + lane] = dz[tile_off(half * 64 + sg * 4 + si, fg * 8 + fi, RSL_H)];
         }
         tc_gemm_acc(c, inT, dzT, 64, half > 0);
     }
-    const int r = threadIdx.x;
+    // read the accumulator out through shared memory (the transposed tiles are dead now) so that the global writes are coalesced:
+    // a thread owns an accumulator ROW, and row-per-thread stores to the row-major partial hit 32 different 256-byte rows at once
+    const int r = threadIdx.x & 127, c0 = (threadIdx.x >> 7) * 32;
     float o[32];
+    rstc::tmem_ld32(c.tmem, c0, o);
+    float* stg = t.w0t;                                   // [128][65] floats: spans the W0^T and W1^T operand tiles (48 KB)
 #pragma unroll
-    for (int c0 = 0; c0 < RSL_H; c0 += 32) {
-        rstc::tmem_ld32(c.tmem, c0, o);
-        if (r < nf_valid) {
-#pragma unroll
-            for (int q = 0; q < 32; q++) gw[(size_t)r * RSL_H + c0 + q] = o[q];      // (the per-block partial is only 4-byte aligned: P is odd)
-        } else if (r == ones_row) {
-#pragma unroll
-            for (int q = 0; q < 32; q++) gb[c0 + q] = o[q];
-        }
-    }
+    for (int q = 0; q < 32; q++) stg[r * 65 + c0 + q] = o[q];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf_valid * RSL_H; i += blockDim.x) gw[i] = stg[(i >> 6) * 65 + (i & 63)];
+    if (threadIdx.x < RSL_H) gb[threadIdx.x] = stg[ones_row * 65 + threadIdx.x];
+    __syncthreads();
 }
 
 // dZ1 = relu'(H1) * (dZ2 * W1^T): GEMM B2 on the tensor core, mask epilogue, written in place of H1
 __device__ __forceinline__ void tc_backprop_hidden(TcCtx& c, const TcTile& t) {
     tc_gemm(c, t.h2, t.w1n, RSL_H);                     // A = dZ2 (in the h2 tile), B rows = input unit i, K = output unit j
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127, c0 = (threadIdx.x >> 7) * 32;
     float o[32];
+    rstc::tmem_ld32(c.tmem, c0, o);
 #pragma unroll
-    for (int c0 = 0; c0 < RSL_H; c0 += 32) {
-        rstc::tmem_ld32(c.tmem, c0, o);
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-            float4* p = reinterpret_cast<float4*>(t.h1 + tile_off(r, c0 + q, RSL_H));
-            float4 h = *p;
-            *p = make_float4(h.x > 0.f ? o[q] : 0.f, h.y > 0.f ? o[q + 1] : 0.f, h.z > 0.f ? o[q + 2] : 0.f, h.w > 0.f ? o[q + 3] : 0.f);
-        }
+    for (int q = 0; q < 32; q += 4) {
+        float4* p = reinterpret_cast<float4*>(t.h1 + tile_off(r, c0 + q, RSL_H));
+        float4 h = *p;
+        *p = make_float4(h.x > 0.f ? o[q] : 0.f, h.y > 0.f ? o[q + 1] : 0.f, h.z > 0.f ? o[q + 2] : 0.f, h.w > 0.f ? o[q + 3] : 0.f);
     }
 }
 
 // one block = 128 samples: same contract as k_ppo_tile (per-block partial gradients and stat partials)
-__global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
+__global__ void __launch_bounds__(RSL_TC_THREADS) k_ppo_tile_tc(PPOArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
@@ -313,9 +324,9 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     TcTile t = tc_carve(smem, D);
     TcCtx c;
     tc_begin(c, &bar, &slot);
-    const int row0 = blockIdx.x * RSL_TILE, r = threadIdx.x, g = row0 + r;
+    const int row0 = blockIdx.x * RSL_TILE, r = threadIdx.x & 127, ch = threadIdx.x >> 7, g = row0 + r;
     const int rows = min(RSL_TILE, a.n - row0);
-    const bool live = g < a.n;
+    const bool live = ch == 0 && g < a.n;          // the per-sample scalar work (loss, statistics) belongs to the ch == 0 thread of a row
     const int s = live ? (a.idx ? a.idx[g] : g) : 0;
     float* gp = a.gpart + (size_t)blockIdx.x * L.P;
     // (no zero fill of the partial: every one of its P entries is written exactly once below)
@@ -359,9 +370,9 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
         gnl *= w * a.inv_n;
         for (int q = 0; q < A; q++) { dmu[q] = gnl * (-z[q] * expf(-ls[q])); dls[q] = gnl * (1.f - z[q] * z[q]); }
     }
-    for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = dmu[q];
-    
+    if (!ch) for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = dmu[q];
     __syncthreads();
+    if (ch) for (int q = 0; q < RSL_HW; q++) dmu[q] = t.dout[r * RSL_DS + q];      // the other column half of the row needs dmu for dZ2
     for (int o = threadIdx.x; o < RSL_H * A; o += blockDim.x) {
         const int k = o / A, q = o - k * A;
         float acc = 0.f;
@@ -370,11 +381,11 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     }
     if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * RSL_DS + threadIdx.x]; gp[L.pi_b + threadIdx.x] = acc; }
     __syncthreads();
-    for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = dls[q];
+    if (!ch) for (int q = 0; q < RSL_HW; q++) t.dout[r * RSL_DS + q] = dls[q];
     __syncthreads();
     if (threadIdx.x < A) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * RSL_DS + threadIdx.x]; gp[L.logstd + threadIdx.x] = acc; }
     // dZ2 = relu'(H2) * (dmu Wp^T), in place of H2 (own row)
-    for (int k = 0; k < RSL_H; k++) {
+    for (int k = 32 * ch; k < 32 * ch + 32; k++) {
         float acc = 0.f;
 #pragma unroll
         for (int q = 0; q < RSL_HW; q++) acc = fmaf(dmu[q], t.wh[k * RSL_HW + q], acc);
@@ -401,12 +412,13 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
         st_vf = 0.5f * err * err;
         dv = a.vf_coef * err * a.inv_n;
     }
-    t.dout[r * RSL_DS] = dv;
+    if (!ch) t.dout[r * RSL_DS] = dv;
     __syncthreads();
+    if (ch) dv = t.dout[r * RSL_DS];
     if (threadIdx.x < RSL_H) { float acc = 0.f; for (int u = 0; u < rows; u++) acc = fmaf(t.h2[tile_off(u, threadIdx.x, RSL_H)], t.dout[u * RSL_DS], acc); gp[L.vf_w + threadIdx.x] = acc; }
     if (threadIdx.x == 64) { float acc = 0.f; for (int u = 0; u < rows; u++) acc += t.dout[u * RSL_DS]; gp[L.vf_b] = acc; }
     __syncthreads();
-    for (int k = 0; k < RSL_H; k++) { float* p = t.h2 + tile_off(r, k, RSL_H); *p = *p > 0.f ? dv * t.wh[k * RSL_HW] : 0.f; }
+    for (int k = 32 * ch; k < 32 * ch + 32; k++) { float* p = t.h2 + tile_off(r, k, RSL_H); *p = *p > 0.f ? dv * t.wh[k * RSL_HW] : 0.f; }
     __syncthreads();
     if (tcw) tc_wgrad(c, t, t.h1, RSL_H, RSL_H, RSL_H, RSL_H, t.h2, gp + L.vf_w1, gp + L.vf_b1);
     else { tc_grad_weight(t.h1, RSL_H, RSL_H, t.h2, gp + L.vf_w1, rows); tc_grad_bias(t.h2, gp + L.vf_b1, rows); }
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile_tc(PPOArgs a) {
     for (int k = 0; k < 4; k++) {
         float x = v4[k];
         for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0) t.dout[k * 4 + (threadIdx.x >> 5)] = x;
+        if ((threadIdx.x & 31) == 0 && threadIdx.x < 128) t.dout[k * 4 + (threadIdx.x >> 5)] = x;
     }
     __syncthreads();
     if (threadIdx.x < 4) a.spart[(size_t)blockIdx.x * 8 + threadIdx.x] = t.dout[threadIdx.x * 4] + t.dout[threadIdx.x * 4 + 1] + t.dout[threadIdx.x * 4 + 2] + t.dout[threadIdx.x * 4 + 3];

@@ -94,9 +94,9 @@ __device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint32_t a_addr, 
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// thread t of the CTA (warp w = t / 32 owns TMEM lanes 32w .. 32w+31) reads row t, columns col0 .. col0+31
+// thread t of the CTA reads accumulator row t % 128 (warp w owns TMEM lanes 32 (w % 4) .. +31), columns col0 .. col0+31
 __device__ __forceinline__ void tmem_ld32(uint32_t tmem_base, int col0, float* out) {
-    const uint32_t taddr = tmem_base + (((threadIdx.x >> 5) * 32u) << 16) + (uint32_t)col0;
+    const uint32_t taddr = tmem_base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16) + (uint32_t)col0;       // warp w may touch lanes 32 (w % 4) .. +31
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
