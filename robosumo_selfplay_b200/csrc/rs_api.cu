@@ -710,32 +710,45 @@ static inline void mt19937_refill(uint32_t* mt) {
     uint32_t y = (mt[623] & UPPER) | (mt[0] & LOWER);
     mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
 }
-static inline uint32_t mt19937_next(uint32_t* mt, int* pos) {
-    if (*pos >= 624) { mt19937_refill(mt); *pos = 0; }
-    uint32_t y = mt[(*pos)++];
-    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-    return y;
-}
+// tempered outputs of the current 624-word block, produced by one vectorisable loop per refill
+struct MtStream {
+    uint32_t* key; int pos; uint32_t out[624];
+    void temper(int from) {
+        for (int i = from; i < 624; i++) {
+            uint32_t y = key[i];
+            y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+            out[i] = y;
+        }
+    }
+    inline uint32_t next() {
+        if (pos >= 624) { mt19937_refill(key); pos = 0; temper(0); }
+        return out[pos++];
+    }
+};
 int rs_legacy_shuffle(uint32_t* key, int* pos, int64_t* x, long long n) {
     if (!key || !pos || !x || n < 0 || *pos < 0 || *pos > 624) return fail(RS_ERR_ARG, "rs_legacy_shuffle: bad argument%s", "");
     if (n > 0x100000000LL) return fail(RS_ERR_UNSUPPORTED, "rs_legacy_shuffle: n beyond the 32-bit interval path%s", "");
+    MtStream g; g.key = key; g.pos = *pos;
+    g.temper(g.pos < 624 ? g.pos : 624);
     // the swap partners depend on the generator only, not on the data: draw them a block ahead and prefetch, so that the random
     // accesses into x (4-64 MB) overlap instead of paying one cache miss per element
     const int B = 64;
     long long jj[B];
+    uint64_t mask = 0;                                       // smallest 2^k - 1 >= i; it only shrinks as i counts down
+    if (n > 1) { mask = (uint64_t)(n - 1); mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32; }
     for (long long i = n - 1; i >= 1; i -= B) {
         const int m = (int)(i >= B ? B : i);                 // partners for i, i-1, ..., i-m+1
         for (int q = 0; q < m; q++) {
             const uint64_t top = (uint64_t)(i - q);
-            uint64_t mask = top;
-            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+            if (top <= (mask >> 1)) mask >>= 1;
             uint64_t j;
-            do { j = (uint64_t)mt19937_next(key, pos) & mask; } while (j > top);
+            do { j = (uint64_t)g.next() & mask; } while (j > top);
             jj[q] = (long long)j;
             __builtin_prefetch(x + j, 1, 0);
         }
         for (int q = 0; q < m; q++) { const long long a = i - q, b = jj[q]; const int64_t tmp = x[a]; x[a] = x[b]; x[b] = tmp; }
     }
+    *pos = g.pos;
     return RS_OK;
 }
 
