@@ -195,7 +195,9 @@ def measure_learner(args, E, local, rank, world, dev):
     runner.run(1, as_numpy=False)                       # warm-up
     runner.nsteps = T
     roll_times = []
-    for rep in range(3):                               # median of three rollouts (a single one occasionally catches a host hiccup)
+    R = None
+    for rep in range(3):                               # median of three rollouts: the first one pays the cudaMalloc of the ~1 GB of
+        R = None                                       # trajectory buffers; afterwards the caching allocator reuses them, as in training
         torch.cuda.synchronize()
         l0 = _lib.lib().rs_launch_count()
         t0 = time.perf_counter()
