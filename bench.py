@@ -388,6 +388,19 @@ def main():
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
         except Exception:
             traffic = None
+    fp32 = None
+    if os.path.exists(tp):
+        try:
+            fpp = float(json.load(open(tp)).get('fp32_flop_per_pair_step'))
+            sm_clock = (clocks or {}).get('sm_mhz') or 1965.0
+            peak_tf = 148 * 128 * 2 * sm_clock * 1e6 / 1e12
+            ach_tf = fpp * E * world / (ms_per_step / 1e3) / 1e12
+            fp32 = {'achieved': ach_tf, 'peak': peak_tf * world, 'unit': 'TFLOP/s', 'frac': ach_tf / (peak_tf * world), 'flop_per_unit': fpp,
+                    'note': 'useful (predicated-on) FP32 FLOP per pair-step from the committed ncu capture (profiles/k_step_traffic.json) against '
+                            '148 SMs x 128 lanes x 2 x SM clock: the kernel is bound by dependent-instruction latency and the slowest warp of a block, '
+                            'with 12.5 of 32 lanes active on average'}
+        except Exception:
+            fp32 = None
     cores = os.cpu_count() or 1
     cpu_rate, cpu_n, cpu_el = cpu_port_rate(args.cpu_seconds, 16 * cores, cores)
     line = {
@@ -401,6 +414,7 @@ def main():
                    'timing': 'CUDA events per step on the launch stream, summed; max over ranks'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_unit': ALGO_BYTES_PER_PAIR_STEP,
+                     'fp32': fp32,
                      'note': 'state stays in shared memory for all 20 forward evaluations; the kernel is FP32-latency/'
                              'issue bound by construction, so the HBM fraction is low (DESIGN.md)'},
         'cpu_baseline': {'value': cpu_rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
