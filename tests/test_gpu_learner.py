@@ -288,3 +288,64 @@ def test_mixed_morphology_pair_physics(oracle_models):
         gq, gv, _, _ = env.get_state()
         assert abs(gq.cpu().numpy() - q).max() < 2e-4 and abs(gv.cpu().numpy() - v).max() < 5e-3, t
     assert torch.equal(oa[:, :15], gq[:, :15]) and torch.equal(ob[:, :19], gq[:, 15:34]) and torch.equal(oa[:, 107:114], gq[:, 15:22])
+
+
+def test_full_size_vtrace_and_gradient_properties():
+    """BASELINE config 2 sizes (E = 4096, T = 128 -> 524 288 samples, minibatch 16 384): properties that do not need the CPU oracle.
+    (a) V-trace with rho = c = 1 (agent 0) is the GAE(lambda) return recursion -- checked against a float64 torch scan on the device;
+        for agent 1 the IS-clipped recursion, same scan.  (b) The minibatch gradient is a SUM over samples: permuting the minibatch
+        or splitting it in two calls changes it only by fp32 summation order (fp32 and tcgen05/tf32 paths alike)."""
+    import ctypes
+    import torch
+    from robosumo_selfplay_b200.runner import Runner
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200 import _lib
+    T, E = 128, 4096
+    g = torch.Generator(device='cuda'); g.manual_seed(3)
+    rn = lambda *s: torch.randn(*s, device='cuda', generator=g)
+    shaping, main = rn(2, T, E).double(), (rn(2, T, E) > 2.0).double() * 2000.0
+    values, nlp, opp = rn(2, T, E), 8 + rn(2, T, E), 8 + rn(2, T, E)
+    dones = (torch.rand(2, T, E, device='cuda', generator=g) < 0.02).to(torch.uint8); dones[1] = dones[0]
+    last_v, last_d = rn(2, E), (torch.rand(E, 2, device='cuda', generator=g) < 0.02).to(torch.uint8)
+    R = Runner.__new__(Runner)
+    R.torch = torch; R.device = torch.device('cuda'); R.gamma, R.lam, R.rho_bar, R.c_bar = 0.995, 0.95, 10.0, 1.0
+    R.anneal_bound = 1000; R._L = _lib.lib()
+    rew, ret, ratios = R.postprocess(300, shaping, main, values, nlp, opp, dones, last_v, last_d)
+    alpha = float(np.linspace(1, 0, 1000)[299])
+    r64 = (alpha * shaping + (1 - alpha) * main).float().double()
+    ratio = (torch.exp(opp[1].double() - nlp[1].double()) * torch.exp(nlp[0].double() - opp[0].double())).float().double()
+    for a in range(2):
+        rho = torch.ones(T, E, device='cuda', dtype=torch.float64) if a == 0 else torch.clamp(ratio, max=10.0)
+        cc = 0.95 * (torch.ones_like(rho) if a == 0 else torch.clamp(ratio, max=1.0))
+        acc = torch.zeros(E, device='cuda', dtype=torch.float64)
+        want = torch.empty(T, E, device='cuda', dtype=torch.float64)
+        for t_ in range(T - 1, -1, -1):
+            nt = 1.0 - (last_d[:, a].double() if t_ == T - 1 else dones[a, t_ + 1].double())
+            nv = (last_v[a] if t_ == T - 1 else values[a, t_ + 1])
+            gv = (torch.tensor(0.995, dtype=torch.float32, device='cuda') * nv).double()          # the reference multiplies in float32
+            delta = rho[t_] * (r64[a, t_] + gv * nt - values[a, t_].double())
+            acc = delta + 0.995 * nt * cc[t_] * acc
+            want[t_] = values[a, t_].double() + acc
+        err = (ret[a].double() - want).abs().max().item()
+        assert err <= 3e-7 * want.abs().max().item() + 1e-5, (a, err)
+    # (b) gradient additivity / permutation invariance at the full minibatch size
+    N, D_, A_, nb = T * E, 121, 8, 16384
+    obs = rn(N, D_); act = 0.5 * rn(N, A_); retn = 2 * rn(N); val = rn(N); old = 8 + rn(N)
+    idx = torch.randperm(N, device='cuda', generator=g).int()[:nb].contiguous()
+    L = _lib.lib(); p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None else None
+    for precision in ('fp32', 'tf32'):
+        np.random.seed(9)
+        m = PPOModel(ob_dim=D_, ac_dim=A_, precision=precision)
+        ws = m._workspace(nb)
+        _lib.check(L.rs_adv_moments(p(idx), nb, p(retn), p(val), p(m.adv_sums), None))
+        def grad(ix):
+            _lib.check(L.rs_ppo_grad(p(m.params), D_, A_, p(obs), p(act), p(retn), p(val), p(old), None, p(ix), ix.numel(), nb, p(m.adv_sums), 0.2, 0.0, 0.5,
+                                     p(ws), p(m.grad_stats), None, 1 if precision == 'tf32' else 0, None))
+            torch.cuda.synchronize()
+            return m.grad_stats[:m.P + 4].double().clone()
+        full = grad(idx)
+        perm = grad(idx[torch.randperm(nb, device='cuda', generator=g)].contiguous())
+        parts = grad(idx[:5000].contiguous()) + grad(idx[5000:].contiguous())
+        scale = full[:m.P].abs().max().item()
+        assert (full - perm)[:m.P].abs().max().item() < 2e-6 * scale and (full - parts)[:m.P].abs().max().item() < 2e-6 * scale, precision
+        assert (full - parts)[m.P:].abs().max().item() < 1e-3 * full[m.P:].abs().max().item()          # the four stat sums add up too
