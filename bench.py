@@ -247,7 +247,7 @@ def measure_learner(args, E, local, rank, world, dev):
     roll_s, upd_s, upd_loop_s = float(tt[0]), float(tt[1]), float(tt[2])
     flops = 114.6e3 * N * nep
     return {'rollout': {'value': E * world * T / roll_s, 'unit': 'env-steps/s', 'T': T, 'launches_per_step': roll_launches / T,
-                        'rollout_seconds': roll_times, 'note': 'Runner.run: 1 fused MLP launch (4 policy evaluations, tcgen05 tf32) + 1 sampling launch + 1 physics launch per step, no host sync; median of 3 rollouts'},
+                        'rollout_seconds': roll_times, 'note': 'Runner.run -> rs_rollout: T steps behind one library call; per step 1 MLP launch (4 policy evaluations, tcgen05 tf32), 1 sampling launch, 1 physics launch and 2 trajectory-write launches, no host work in between; median of 3 rollouts'},
             'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
                            'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_s / 1e12,
                            'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,

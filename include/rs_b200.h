@@ -116,6 +116,21 @@ int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* log
                       float* actions, float* nlp0, float* nlp1, float* opp_nlp0, float* opp_nlp1, void* stream);
 /* DiagGaussianPd.neglogp (distributions.py:238-241) */
 int rs_neglogp(int n, int act_dim, const float* act, const float* mu, const float* logstd, float* out, void* stream);
+/* Runner.run's step loop (runner.py:62-104) for a symmetric pair, T steps enqueued by ONE call: per step the four policy
+ * evaluations (one launch), the trajectory writes of the observation / done flags, action sampling with the four neglogps, the
+ * physics step with auto-reset, and the trajectory writes of the reward terms and episode records -- 5 launches, no host work.
+ * All pointers are device pointers.  `obs`, `done` hold the current observation / done flags on entry and the last ones on exit
+ * (they are the env's own output buffers).  Trajectory arrays are time-major: mb_obs [2][T][E][D], mb_actions [T][E][2][A],
+ * mb_values / mb_nlp / mb_opp_nlp / mb_shaping / mb_main [2][T][E], mb_dones [2][T][E] u8, ep_done [T][E] u8, ep_info [T][E][3];
+ * scratch: 4*E*A floats.  Sampling noise is Philox keyed by (seed, tick0 + t). */
+typedef struct rs_rollout_io {
+    const float* params0; const float* params1;                 /* learner (agent 0) and opponent (agent 1), flat parameter vectors */
+    float* obs; float* rew; uint8_t* done; float* info; float* episode;
+    float* mb_obs; float* mb_actions; float* mb_values; float* mb_nlp; float* mb_opp_nlp; uint8_t* mb_dones;
+    float* mb_shaping; float* mb_main; uint8_t* ep_done; float* ep_info; float* scratch;
+} rs_rollout_io;
+int rs_rollout(rs_env* h, int T, const rs_rollout_io* io, int precision, unsigned long long seed, unsigned int tick0, int deterministic,
+               void* stream);
 /* V-trace returns and IS ratios (runner.py:166-200); arrays [2][T][E], last_values [2][E], last_dones [E][2], ratios [3][T][E] */
 int rs_vtrace(int T, int E, float gamma, float lam, float rho_bar, float c_bar, const float* rewards, const float* values,
               const uint8_t* dones, const float* nlp, const float* opp_nlp, const float* last_values, const uint8_t* last_dones,

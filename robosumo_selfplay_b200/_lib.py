@@ -27,6 +27,11 @@ class rs_mlp_job(ctypes.Structure):
 
 
 # every symbol include/rs_b200.h declares: name -> (restype, argtypes)
+class rs_rollout_io(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in ('params0', 'params1', 'obs', 'rew', 'done', 'info', 'episode', 'mb_obs', 'mb_actions', 'mb_values', 'mb_nlp',
+                                        'mb_opp_nlp', 'mb_dones', 'mb_shaping', 'mb_main', 'ep_done', 'ep_info', 'scratch')]
+
+
 SYMBOLS = {
     'rs_agent_model_size': (c_int, []),
     'rs_last_error': (ctypes.c_char_p, []),
@@ -45,6 +50,7 @@ SYMBOLS = {
     'rs_param_count': (c_int, [c_int, c_int]),
     'rs_mlp_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'rs_mlp_forward_multi': (c_int, [ctypes.POINTER(rs_mlp_job), c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'rs_rollout': (c_int, [c_void_p, c_int, ctypes.POINTER(rs_rollout_io), c_int, ctypes.c_ulonglong, ctypes.c_uint, c_int, c_void_p]),
     'rs_rollout_sample': (c_int, [c_int, c_int] + [c_void_p] * 6 + [ctypes.c_ulonglong, ctypes.c_uint, c_int] + [c_void_p] * 6),
     'rs_neglogp': (c_int, [c_int, c_int] + [c_void_p] * 5),
     'rs_vtrace': (c_int, [c_int, c_int, c_float, c_float, c_float, c_float] + [c_void_p] * 10),

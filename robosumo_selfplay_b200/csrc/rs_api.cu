@@ -595,6 +595,44 @@ int rs_rollout_sample(int E, int act_dim, const float* logstd0, const float* log
     return RS_OK;
 }
 
+int rs_rollout(rs_env* h, int T, const rs_rollout_io* io, int precision, unsigned long long seed, unsigned int tick0, int deterministic,
+               void* stream) {
+    if (!h || !io || T <= 0 || !io->params0 || !io->params1 || !io->obs || !io->rew || !io->done || !io->info || !io->episode || !io->mb_obs ||
+        !io->mb_actions || !io->mb_values || !io->mb_nlp || !io->mb_opp_nlp || !io->mb_dones || !io->mb_shaping || !io->mb_main || !io->ep_done ||
+        !io->ep_info || !io->scratch)
+        return fail(RS_ERR_ARG, "rs_rollout: bad argument%s", "");
+    if (h->obsA != h->obsB || h->LA != h->LB) return fail(RS_ERR_UNSUPPORTED, "rs_rollout: the two agents must share one observation / action layout%s", "");
+    const int E = h->d.E, D = h->obsA, A = h->nu / 2;
+    const rsl::Layout L = rsl::make_layout(D, A);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t TE = (size_t)T * E;
+    float* mu00 = io->scratch; float* mu10 = mu00 + (size_t)E * A; float* mu11 = mu10 + (size_t)E * A; float* mu01 = mu11 + (size_t)E * A;
+    for (int t = 0; t < T; t++) {
+        rsl::MlpJobs J;
+        memset(&J, 0, sizeof(J));
+        // models[0].step(obs[:,0]) | models[1].action_probability(obs[:,0], a0) | models[1].step(obs[:,1]) | models[0].value + action_probability(obs[:,1], a1)
+        const float* prm[4] = { io->params0, io->params1, io->params1, io->params0 };
+        float* means[4] = { mu00, mu10, mu11, mu01 };
+        float* vals[4] = { io->mb_values + (size_t)t * E, nullptr, nullptr, io->mb_values + TE + (size_t)t * E };
+        for (int j = 0; j < 4; j++) { J.params[j] = prm[j]; J.X[j] = io->obs + (j >= 2 ? D : 0); J.ldx[j] = (size_t)2 * D; J.mean[j] = means[j]; J.value[j] = vals[j]; J.act[j] = 0; }
+        int rc = mlp_forward_jobs(J, 4, D, A, E, precision, stream);
+        if (rc) return rc;
+        const long long n_obs = (long long)E * 2 * D;
+        rsl::k_traj_pre<<<(unsigned)((n_obs + 255) / 256), 256, 0, st>>>(E, D, t, T, io->obs, io->done, io->mb_obs, io->mb_dones);
+        g_launches++;
+        float* act = io->mb_actions + (size_t)t * E * 2 * A;
+        rc = rs_rollout_sample(E, A, io->params0 + L.logstd, io->params1 + L.logstd, mu00, mu10, mu11, mu01, seed, tick0 + (unsigned)t, deterministic, act,
+                               io->mb_nlp + (size_t)t * E, io->mb_nlp + TE + (size_t)t * E, io->mb_opp_nlp + (size_t)t * E, io->mb_opp_nlp + TE + (size_t)t * E, stream);
+        if (rc) return rc;
+        rc = rs_step(h, act, io->obs, io->rew, io->done, io->info, io->episode, 1, stream);
+        if (rc) return rc;
+        rsl::k_traj_post<<<(E + 127) / 128, 128, 0, st>>>(E, t, T, io->info, io->done, io->episode, io->mb_shaping, io->mb_main, io->ep_done, io->ep_info);
+        g_launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+
 int rs_neglogp(int n, int act_dim, const float* act, const float* mu, const float* logstd, float* out, void* stream) {
     if (n <= 0 || act_dim > 16) return fail(RS_ERR_ARG, "rs_neglogp: bad argument%s", "");
     rsl::k_neglogp<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, act_dim, act, mu, logstd, out);

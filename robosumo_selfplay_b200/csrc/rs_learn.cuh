@@ -509,6 +509,29 @@ __global__ void k_adam(float* __restrict__ params, float* __restrict__ m, float*
     params[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// trajectory writes of one rollout step (runner.py:70-72,95-100): before the env step the observation and done flags the policies
+// acted on, after it the reward terms and the episode records
+__global__ void k_traj_pre(int E, int D, int t, int T, const float* __restrict__ obs, const uint8_t* __restrict__ done,
+                           float* __restrict__ mb_obs, uint8_t* __restrict__ mb_dones) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [E][2][D]
+    if (i >= (long long)E * 2 * D) return;
+    const int k = (int)(i % D), a = (int)((i / D) & 1);
+    const long long e = i / (2 * D);
+    mb_obs[(((long long)a * T + t) * E + e) * D + k] = obs[i];
+    if (k == 0) mb_dones[((long long)a * T + t) * E + e] = done[2 * e + a];
+}
+__global__ void k_traj_post(int E, int t, int T, const float* __restrict__ info, const uint8_t* __restrict__ done, const float* __restrict__ epi,
+                            float* __restrict__ mb_shaping, float* __restrict__ mb_main, uint8_t* __restrict__ ep_done, float* __restrict__ ep_info) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    for (int a = 0; a < 2; a++) {
+        mb_shaping[((long long)a * T + t) * E + e] = info[(e * 2 + a) * RS_INFO_DIM + 6];
+        mb_main[((long long)a * T + t) * E + e] = info[(e * 2 + a) * RS_INFO_DIM + 3];
+    }
+    ep_done[(long long)t * E + e] = done[2 * e];
+    for (int k = 0; k < 3; k++) ep_info[((long long)t * E + e) * 3 + k] = epi[e * 3 + k];
+}
+
 // [pg_loss, vf_loss, entropy, approxkl, clipfrac] (model.py:137): means of the four stat sums stored behind the gradient, and the
 // DiagGaussian entropy sum(logstd + 0.5 log(2 pi e)) (distributions.py:244-245) of the parameters as they are now
 __global__ void k_ppo_stats(const float* __restrict__ grad_stats, const float* __restrict__ params, int P, int logstd_off, int A,

@@ -44,6 +44,7 @@ class Runner:
         self._L = _lib.lib()
         self._seed = seed
         self._tick = 0
+        self.use_fused = True           # device env: run the step loop through rs_rollout (one library call); False = step by step
         self.tstart = time.time()
 
     def _to_dev(self, x, dtype=None):
@@ -87,7 +88,25 @@ class Runner:
             jobs[k].params = mm.params.data_ptr(); jobs[k].obs_row_stride = stride
             jobs[k].mean = mu.data_ptr(); jobs[k].value = vv.data_ptr() if vv is not None else None
         prec = 1 if m0.precision == 'tf32' else 0
-        for step in range(T):
+        fused = self.use_fused and self.device_env and getattr(self.env, 'auto_reset', False) and not getattr(self.env, 'mixed', False)
+        if fused:
+            # the whole step loop in ONE library call (rs_rollout): per step the four policy evaluations, the trajectory writes, the
+            # action sampling, the physics step and the reward / episode records -- 5 launches, no host work between them.  The
+            # env's own output buffers carry the observation and done flags from step to step.
+            env = self.env
+            env.d_obs.copy_(self.obs.reshape(env.d_obs.shape)); env.d_done.copy_(self.dones)
+            io = _lib.rs_rollout_io()
+            scratch = t.empty((4, E, A), **f32)
+            for k, v in (('params0', m0.params), ('params1', m1.params), ('obs', env.d_obs), ('rew', env.d_rew), ('done', env.d_done), ('info', env.d_info),
+                         ('episode', env.d_epi), ('mb_obs', mb_obs), ('mb_actions', mb_actions), ('mb_values', mb_values), ('mb_nlp', mb_nlp),
+                         ('mb_opp_nlp', mb_opp_nlp), ('mb_dones', mb_dones), ('mb_shaping', mb_shaping), ('mb_main', mb_main), ('ep_done', ep_done),
+                         ('ep_info', ep_info), ('scratch', scratch)):
+                assert v.is_contiguous()
+                setattr(io, k, v.data_ptr())
+            _lib.check(self._L.rs_rollout(env._h, T, ctypes.byref(io), prec, self._seed, self._tick, 1 if deterministic else 0, self._stream()))
+            self._tick += T
+            self.obs.copy_(env.d_obs.reshape(self.obs.shape)); self.dones.copy_(env.d_done)
+        for step in (range(T) if not fused else ()):
             o0, o1 = self.obs[:, 0, :], self.obs[:, 1, :]
             # the four policy evaluations of runner.py:67-90 in ONE launch (blockIdx.y = job):
             #   models[0].step(obs[:,0]) | models[1].action_probability(obs[:,0], a0) | models[1].step(obs[:,1]) |

@@ -349,3 +349,31 @@ def test_full_size_vtrace_and_gradient_properties():
         scale = full[:m.P].abs().max().item()
         assert (full - perm)[:m.P].abs().max().item() < 2e-6 * scale and (full - parts)[:m.P].abs().max().item() < 2e-6 * scale, precision
         assert (full - parts)[m.P:].abs().max().item() < 1e-3 * full[m.P:].abs().max().item()          # the four stat sums add up too
+
+
+def test_fused_rollout_equals_step_by_step_loop():
+    """rs_rollout (T steps behind one library call) against the step-by-step loop of Runner.run on twin envs: every trajectory
+    array, the IS ratios, the returns and the carried observation are bit-identical."""
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200.runner import Runner
+    E, T = 96, 40
+    np.random.seed(2)
+    models = [PPOModel(ob_dim=D, ac_dim=A), PPOModel(ob_dim=D, ac_dim=A, trainable=False)]
+    outs = []
+    for fused in (True, False):
+        env = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E, seed=31, device_api=True)
+        r = Runner(env=env, models=models, nsteps=T, gamma=0.995, lam=1.0, rho_bar=10.0, c_bar=1.0, anneal_bound=1000, seed=5)
+        r.use_fused = fused
+        a = r.run(3, as_numpy=False)
+        b = r.run(4, as_numpy=False)                    # second rollout continues from the carried obs / dones / noise counter
+        outs.append((a, b, r.obs.clone(), r.dones.clone()))
+        env.close()
+    (fa, fb, fo, fd), (sa, sb, so, sd) = outs
+    for x, y in ((fa, sa), (fb, sb)):
+        for k in ('obs', 'returns', 'dones', 'actions', 'values', 'neglogpacs', 'rewards', 'opponent_neglogpacs', 'opponent_obs', 'opponent_actions',
+                  'off_policy_ratio', 'off_env_ratio', 'ratio'):
+            assert torch.equal(x[k], y[k]), k
+        assert x['epinfos'] is not None and [(e['r'], e['l']) for e in x['epinfos']] == [(e['r'], e['l']) for e in y['epinfos']]
+    assert torch.equal(fo, so) and torch.equal(fd, sd)
