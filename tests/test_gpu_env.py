@@ -147,3 +147,22 @@ def test_host_entry_point_pinned_and_pageable_buffers_agree():
         np.testing.assert_array_equal(dn, done.astype(bool))
         np.testing.assert_array_equal(obs, od.cpu().numpy())
         np.testing.assert_array_equal(rew, rd.cpu().numpy())
+
+
+@pytest.mark.parametrize('E', [1, 27, 29, 4097])
+def test_ragged_batch_sizes(E):
+    """Batch sizes that do not fill a block (1, 27), straddle one (29) or spill one pair into a second wave (4097): same
+    results as the first E pairs of a larger batch with the same states (an env never depends on its neighbours)."""
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    big = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E + 5, seed=77, device_api=True, auto_reset=False)
+    big.reset()
+    q, v, _, _ = big.get_state()
+    env = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E, seed=1, device_api=True, auto_reset=False)
+    env.reset(); env.set_state(q[:E], v[:E]); big.set_state(q, v)
+    g = torch.Generator(device='cuda'); g.manual_seed(E)
+    for t in range(3):
+        a = torch.randn(E + 5, 2, 8, device='cuda', generator=g)
+        ob, rb, db, _ = big.step(a)
+        o, r, d, _ = env.step(a[:E].contiguous())
+        assert torch.isfinite(o).all() and torch.equal(o, ob[:E]) and torch.equal(r, rb[:E]) and torch.equal(d, db[:E])
