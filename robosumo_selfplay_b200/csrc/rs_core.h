@@ -668,7 +668,7 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
     const float tc = fmaxf(0.02f, 2.f * c.h);
-    const float Kc = 1.f / (RS_DMAX * RS_DMAX * tc * tc), Bc = 2.f / (RS_DMAX * tc);
+    const float Kc = 1.f / (RS_DMAX * RS_DMAX * tc * tc);
     // limits first: sign and D, then J v through rows_of
     if (RS_LANE0) { s.pmask = 0; s.pvalid = 0; }
     RS_SYNC();
@@ -687,12 +687,11 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         float diag = isank ? m.iwd_ank[l] : m.iwd_hip[l];
         float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
         s.lD[j] = sgn != 0.f ? 1.f / R : 0.f;
-        s.laref[j] = -Kc * imp * pos;           // velocity term added below
+        s.laref[j] = -Kc * imp * pos;           // position term only (see the note on aref below)
     }
-    RS_SYNC();
-    twists(c, s.v);
-    rows_of(c, s.v, s.cjd, s.ljd);              // J v (scratch in cjd / ljd)
-    RS_LANE_LOOP(j, S::NU) { s.laref[j] -= Bc * s.ljd[j]; }
+    // aref = -B (J v) - K imp pos.  Only its position term is stored: the residual the solver starts from,
+    //   jar = J x0 - aref = J (x0 + B v) + K imp pos,
+    // takes ONE pass of twists + rows_of over the vector x0 + B v (solve(), first pass) instead of one for J v here and one for J x0 there
     RS_LANE_LOOP(k, s.ncon) {
         float pm = s.cD[k] - RS_MARGIN;
         float imp = impedance(pm);
@@ -700,9 +699,13 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
         R = 2.f * RS_MU * RS_MU * R;
         s.cD[k] = 1.f / R;
-        for (int r = 0; r < 4; r++) s.caref[k][r] = -Bc * s.cjd[k][r] - Kc * imp * pm;
+        for (int r = 0; r < 4; r++) s.caref[k][r] = -Kc * imp * pm;
     }
     RS_SYNC();
+}
+RS_HD float solref_damping(float h) {        // B of mj_makeImpedance for solref (0.02, 1): 2 / (dmax * timeconst)
+    const float tc = fmaxf(0.02f, 2.f * h);
+    return 2.f / (RS_DMAX * tc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1158,9 +1161,14 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         RS_ACC(2);
         RS_PHASE_SYNC();
         if (conv) continue;
+        if (first) {     // residual pass: rows of J (x0 + B v), see make_constraints (s.d is free until the first Newton direction)
+            const float Bc = solref_damping(c.h);
+            RS_LANE_LOOP(i, S::NV) { s.d[i] = s.x[i] + Bc * s.v[i]; }
+            RS_SYNC();
+        }
         const float* vec = first ? s.x : s.d;
-        twists(c, vec);
-        rows_of(c, vec, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
+        twists(c, s.d);
+        rows_of(c, s.d, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
         mat_vec(c, vec, first ? s.r : s.Md, first ? s.r : (const float*)0);     // first: r = M x0 - qfrc_smooth
         RS_ACC(3);
         if (first) {
