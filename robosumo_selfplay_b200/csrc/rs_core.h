@@ -1166,12 +1166,11 @@ RS_HD void solve(Ctx<LA, LB>& c) {
             RS_LANE_LOOP(i, S::NV) { s.d[i] = s.x[i] + Bc * s.v[i]; }
             RS_SYNC();
         }
-        const float* vec = first ? s.x : s.d;
         twists(c, s.d);
         rows_of(c, s.d, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
-        mat_vec(c, vec, first ? s.r : s.Md, first ? s.r : (const float*)0);     // first: r = M x0 - qfrc_smooth
         RS_ACC(3);
         if (first) {
+            mat_vec(c, s.x, s.r, s.r);                         // r = M x0 - qfrc_smooth
             RS_LANE_LOOP(k, s.ncon) {
                 // rows of the same geom pair at the previous evaluation's solution predict this evaluation's active rows
                 int bits = 16;
@@ -1199,16 +1198,23 @@ RS_HD void solve(Ctx<LA, LB>& c) {
         RS_LANE_LOOP(j, S::NU) {
             if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
         }
-        // was the set used for this iteration the sign set at the current point?  (not when it came from the prediction)
-        if (RS_LANE0) s.pvalid = 0;
         RS_SYNC();
-        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] < 0.f))) s.pvalid = 1; }
-        RS_LANE_LOOP(k, s.ncon) {
-            const int act = s.cact(k);
-            for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] < 0.f)) s.pvalid = 1;
+        const int same = s.same;
+        int predicted = 0;
+        if (!same) {
+            // the full step leaves the active set: the iteration goes on from x + alpha d and needs M d (for r and the line search).
+            // Was the set used for this iteration the sign set at the current point?  (not when it came from the prediction)
+            if (RS_LANE0) s.pvalid = 0;
+            RS_SYNC();
+            RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] < 0.f))) s.pvalid = 1; }
+            RS_LANE_LOOP(k, s.ncon) {
+                const int act = s.cact(k);
+                for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] < 0.f)) s.pvalid = 1;
+            }
+            RS_SYNC();
+            predicted = s.pvalid;
+            mat_vec(c, s.d, s.Md, (const float*)0);
         }
-        RS_SYNC();
-        const int same = s.same, predicted = s.pvalid;
         float alpha = 1.f;
         if (!same && !predicted) {
             // exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton inside a bracket
@@ -1226,7 +1232,8 @@ RS_HD void solve(Ctx<LA, LB>& c) {
                 alpha = an;
             }
         }
-        RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; }
+        if (same) { RS_LANE_LOOP(i, S::NV) { s.x[i] += s.d[i]; } }       // converged: r is not needed any more, M d was never formed
+        else { RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; } }
         RS_LANE_LOOP(k, s.ncon) {
             int sign = 0;
             for (int r = 0; r < 4; r++) { s.cjar[k][r] += alpha * s.cjd[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
