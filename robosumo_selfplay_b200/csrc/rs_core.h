@@ -522,6 +522,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
     // --- agent 0 geoms against agent 1 geoms ---
     {
         V3 dt = ld3(s.org[1]) - ld3(s.org[0]);
+        // (a tighter bound from the actual geom extents was measured: it skips the pair loop more often but does not pay for its atomics)
         float reach = c.am[0].reach + c.am[1].reach + RS_MARGIN;
         if (dot(dt, dt) < reach * reach) {
             RS_LANE_LOOP(p, S::NGA * S::NGB) {
@@ -969,9 +970,9 @@ RS_HD void arrow_solve(Ctx<LA, LB>& c) {
     // Schur complement onto the floating base, upper triangle + right-hand side (27 entries per agent), mirrored
     RS_LANE_LOOP(e, 54) {
         const int a = e >= 27 ? 1 : 0, t = e - 27 * a;
-        int r = 0, cc = t;                                   // t -> (r, cc) with r <= cc <= 6: rows of length 7, 6, 5, ...
-        while (cc >= 7 - r) { cc -= 7 - r; r++; }
-        cc += r;
+        // t -> (r, cc) with r <= cc <= 6: rows of length 7, 6, 5, 4, 3, 2 start at t = 0, 7, 13, 18, 22, 25
+        const int r = (t >= 7) + (t >= 13) + (t >= 18) + (t >= 22) + (t >= 25);
+        const int cc = t - (7 * r - ((r * (r - 1)) >> 1)) + r;
         float acc;
         const int l0 = c.leg0(a), va = c.vadr(a);
         if (cc < 6) {
