@@ -866,11 +866,48 @@ RS_HD void build_H(Ctx<LA, LB>& c) {
 // back-substitution.  One warp barrier per pivot.  When no inter-agent contact couples the agents
 // H is block diagonal and both per-agent blocks are eliminated in the same pass (half the pivots,
 // half the columns).
+#if defined(__CUDA_ARCH__)
+// The same elimination with the matrix rows in REGISTERS (N <= 32: lane j owns row j, fully unrolled so that every register
+// index is static) and the pivot row broadcast by warp shuffles: no shared-memory round trip and no barrier per pivot.  A pair
+// with an inter-agent contact is the straggler of its block (its warp runs alone while 27 others wait at the evaluation
+// barrier), so what counts here is the latency of ONE warp: 28 pivots cost ~2 k cycles this way against ~28 k through shared
+// memory (tools/pair_cost_profile.py).  Same operations in the same order as the loop below: bit-identical results.
+template <int N>
+__device__ __forceinline__ void gj_rows_in_registers(const float* Hb, const int ld, float* d) {
+    const int j = threadIdx.x & 31;
+    float row[N + 1];
+#pragma unroll
+    for (int cc = 0; cc < N; cc++) row[cc] = j < N ? Hb[j * ld + cc] : 0.f;
+    row[N] = j < N ? -d[j] : 0.f;
+    float diag = 1.f;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const float pk = __shfl_sync(0xffffffffu, row[k], k);
+        const float f = (j == k) ? 0.f : row[k] * RS_RCP(fmaxf(pk, 1e-12f));
+        if (j == k) diag = pk;
+#pragma unroll
+        for (int cc = k + 1; cc <= N; cc++) row[cc] = fmaf(-f, __shfl_sync(0xffffffffu, row[cc], k), row[cc]);
+    }
+    __syncwarp();
+    if (j < N) d[j] = row[N] * RS_RCP(fmaxf(diag, 1e-12f));
+    __syncwarp();
+}
+#endif
+
 template <int LA, int LB>
 RS_HD void chol_solve(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
     const bool bd = !(s.coupled & 1);
+#if defined(__CUDA_ARCH__) && !defined(RS_NO_REG_GJ)
+    if (!bd) {
+        if constexpr (S::NV <= 32) { gj_rows_in_registers<S::NV>(s.H, S::NVP, s.d); return; }
+    } else if constexpr (LA > 4 || LB > 4) {        // intra-agent contacts exist only for the six- and eight-legged bodies
+        gj_rows_in_registers<S::NVA>(s.H, S::NVA + 1, s.d);
+        gj_rows_in_registers<S::NVB>(s.H + S::BSA, S::NVB + 1, s.d + S::NVA);
+        return;
+    }
+#endif
     const int nk = bd ? (S::NVA > S::NVB ? S::NVA : S::NVB) : S::NV;
     RS_LANE_LOOP(j, S::NV) { s.d[j] = -s.d[j]; }
     RS_SYNC();
