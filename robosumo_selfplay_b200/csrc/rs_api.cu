@@ -9,17 +9,15 @@
 #ifndef RS_WPB
 #define RS_WPB 28  // max warps (env pairs) per block; one block per SM: 28 Ant slabs of 8.2 KB fill the 227 KB (E = 4096 -> one wave)
 #endif
-#ifndef RS_NO_LOCKSTEP
-#define RS_LOCKSTEP 1   // warps of a block re-align at every forward evaluation (instruction-cache locality)
-#endif
-// Re-alignment of the warps of a block (instruction-cache locality vs. waiting for the slowest warp):
-//   RS_SYNC_MODE 0 none, 1 every forward evaluation, 2 every substep (4 evaluations), 3 every evaluation within groups of
-//   RS_SYNC_GROUP warps (named barriers)
+// Re-alignment of the warps of a block (instruction-cache locality vs. waiting for the slowest warp), see simulate() in rs_core.h:
+//   RS_SYNC_MODE 7 (default) once per trip = [evaluation start] + [one Newton iteration] (the per-warp progress machine),
+//                1 once per forward evaluation (round-1 behaviour), 0 never.
+// Measured and dropped in round 1: per substep, named-barrier groups of 4-14 warps, per phase, a one-evaluation sliding window.
 #ifndef RS_SYNC_MODE
-#define RS_SYNC_MODE 1
+#define RS_SYNC_MODE 7
 #endif
-#ifndef RS_SYNC_GROUP
-#define RS_SYNC_GROUP 7
+#if RS_SYNC_MODE != 7
+#define RS_TRIP_MACHINE 0
 #endif
 #ifdef RS_EXPERIMENT_CLOCK
 __device__ long long rs_dbg[4200 * 128];
@@ -27,58 +25,19 @@ extern "C" int rs_debug_read(void* dst, size_t bytes) { return (int)cudaMemcpyFr
 #endif
 __device__ __forceinline__ long long rs_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 #if defined(__CUDA_ARCH__)
-#if RS_SYNC_MODE == 1
+#if RS_SYNC_MODE == 7
+#define RS_TRIP_ANY(p) __syncthreads_or(p)
+#ifndef RS_TRIP_NO_MID
+#define RS_TRIP_SYNC() __syncthreads()
+#endif
+#elif RS_SYNC_MODE == 1
 #define RS_EVAL_SYNC() __syncthreads()
-#elif RS_SYNC_MODE == 2
-#define RS_SUBSTEP_SYNC() __syncthreads()
-#elif RS_SYNC_MODE == 4
-#define RS_SOLVE_SYNC() __syncthreads()
-#elif RS_SYNC_MODE == 5
-#define RS_EVAL_SYNC() __syncthreads()
-#define RS_SOLVE_SYNC() __syncthreads()
-#elif RS_SYNC_MODE == 6
-// sliding window: a warp may run at most one evaluation ahead of the slowest warp of its block (two mbarriers, one per parity)
-#define RS_EVAL_SYNC() rs_window_sync(c.evk)
-__device__ __forceinline__ unsigned long long* rs_win_bars() { __shared__ unsigned long long b[2]; return b; }
-__device__ __forceinline__ void rs_window_init() {
-    if (threadIdx.x == 0) {
-        unsigned long long* b = rs_win_bars();
-        for (int i = 0; i < 2; i++)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(b + i)), "r"(blockDim.x >> 5));
-    }
-}
-__device__ __forceinline__ void rs_window_sync(int& k) {
-    unsigned long long* b = rs_win_bars();
-    if (k >= 1 && (threadIdx.x & 31) == 0) {
-        unsigned long long st;
-        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((unsigned)__cvta_generic_to_shared(b + ((k - 1) & 1))) : "memory");
-    }
-    if (k >= 2) {
-        const unsigned addr = (unsigned)__cvta_generic_to_shared(b + (k & 1)), par = ((k - 2) >> 1) & 1;
-        asm volatile(
-            "{\n\t.reg .pred P1;\n\tWW_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-            "@P1 bra WD_%=;\n\tbra WW_%=;\n\tWD_%=:\n\t}" :: "r"(addr), "r"(par) : "memory");
-    }
-    k++;
-}
-#elif RS_SYNC_MODE == 3
-#define RS_EVAL_SYNC() rs_group_sync()
-__device__ __forceinline__ void rs_group_sync() {
-    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5, g = w / RS_SYNC_GROUP;
-    const int first = g * RS_SYNC_GROUP, cnt = (nw - first < RS_SYNC_GROUP ? nw - first : RS_SYNC_GROUP) * 32;
-    asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "r"(cnt));
-}
 #endif
 #ifdef RS_EXPERIMENT_CLOCK
 #define RS_ACC(i) { __syncwarp(); long long rs_now = rs_clock(); c.acc[i] += rs_now - c.tlast; c.tlast = rs_now; }
 #define RS_CLOCK_BEGIN() { __syncwarp(); if ((threadIdx.x & 31) == 0 && c.evk < 20) rs_dbg[(size_t)c.env * 128 + 3 * c.evk] = rs_clock(); }
 #define RS_CLOCK_MARK(i) { if (i == 2) { __syncwarp(); if ((threadIdx.x & 31) == 0 && c.evk < 20) rs_dbg[(size_t)c.env * 128 + 3 * c.evk + 1] = rs_clock(); } }
 #define RS_CLOCK_END() { __syncwarp(); if ((threadIdx.x & 31) == 0 && c.evk < 20) { rs_dbg[(size_t)c.env * 128 + 3 * c.evk + 2] = rs_clock(); rs_dbg[(size_t)c.env * 128 + 64 + c.evk] = c.s->niter | (c.s->coupled << 8) | (c.s->ncon << 16); } c.evk++; }
-#endif
-#ifdef RS_USE_PHASE_SYNC
-#define RS_PHASE_SYNC() __syncthreads()
-#define RS_BLOCK_ANY(p) __syncthreads_or(p)
 #endif
 #endif
 #define RS_LOCKSTEP 1
@@ -128,10 +87,6 @@ template <int LA, int LB>
 __device__ __forceinline__ Slab<LA, LB>* warp_setup(Ctx<LA, LB>& c, const EnvDev& d, rs_agent_model* sm_am, unsigned char* smem_raw) {
     typedef Slab<LA, LB> S;
     for (int i = threadIdx.x; i < (int)(2 * sizeof(rs_agent_model) / 4); i += blockDim.x) ((int*)sm_am)[i] = ((const int*)d.am)[i];
-#if defined(__CUDA_ARCH__) && RS_SYNC_MODE == 6
-    rs_window_init();
-    c.evk = 0;
-#endif
     __syncthreads();
     S* s = reinterpret_cast<S*>(smem_raw) + (threadIdx.x >> 5);
     c.s = s; c.am = sm_am; c.h = d.h; c.max_newton = d.max_newton;

@@ -1149,12 +1149,10 @@ RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_fwdConstraint: primal Newton, exact line search, warm start from s.x
+// mj_fwdConstraint: primal Newton, exact line search, warm start from s.x.  Split in three so that the warps of a block can
+// re-align per Newton ITERATION (simulate() below): solve_first (residuals at the warm start), solve_iter (one iteration,
+// returns true when the active set survived the full step, i.e. the point is the exact optimum), solve_finish.
 // ------------------------------------------------------------------------------------------
-#ifndef RS_PHASE_SYNC
-#define RS_PHASE_SYNC()          // optional block-wide re-alignment between phases (instruction-cache locality)
-#define RS_BLOCK_ANY(p) (p)
-#endif
 #ifndef RS_ARROW
 #define RS_ARROW 1     // 0: always use the generic (block-diagonal / dense) assembly and elimination
 #endif
@@ -1164,133 +1162,143 @@ RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
 #ifndef RS_SOLVE_TRACE
 #define RS_SOLVE_TRACE(s, it)     // host-emulation analysis hook (tools), empty in every build of the product
 #endif
+// residuals at the warm start x0: jar = J x0 - aref, r = M x0 - tau, and the predicted active sets
 template <int LA, int LB>
-RS_HD void solve(Ctx<LA, LB>& c) {
+RS_HD void solve_first(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    bool conv = false;
-    int it = 0;
-    // iteration -1 only evaluates the residuals at the warm start x0: jar = J x0 - aref, r = M x0 - tau
-    for (int iter = -1; iter < c.max_newton; iter++) {
-        if (!RS_BLOCK_ANY(!conv)) break;
-        const bool first = iter < 0;
-        RS_ACC(5);
-        if (!conv && !first) {
-            // coupling that matters for THIS iteration's H: only contacts with active rows contribute J^T D J, so an inter- or
-            // intra-agent contact that is inside the margin but not loaded does not force the dense paths
-            if (RS_LANE0) s.coupled = 0;
-            RS_SYNC();
-            RS_LANE_LOOP(k, s.ncon) {
-                const int bA = s.bA(k), bB = s.bB(k);
-                if (bA >= 0 && s.cact(k) != 0)
-                    RS_ATOMIC_OR(&s.coupled, ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1 : 2);
-            }
-            RS_SYNC();
-            jt_forces(c);
-            RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
-            RS_SYNC();
-        }
-        RS_ACC(0);
-        RS_PHASE_SYNC();
-        if (!conv && !first) { if (RS_ARROW && s.coupled == 0) build_H_arrow(c); else build_H(c); }
-        RS_ACC(1);
-        RS_PHASE_SYNC();
-        if (!conv && !first) { if (RS_ARROW && s.coupled == 0) arrow_solve(c); else chol_solve(c); }      // s.d = -H^-1 grad
-        RS_ACC(2);
-        RS_PHASE_SYNC();
-        if (conv) continue;
-        if (first) {     // residual pass: rows of J (x0 + B v), see make_constraints (s.d is free until the first Newton direction)
-            const float Bc = solref_damping(c.h);
-            RS_LANE_LOOP(i, S::NV) { s.d[i] = s.x[i] + Bc * s.v[i]; }
-            RS_SYNC();
-        }
-        twists(c, s.d);
-        rows_of(c, s.d, first ? s.cjar : s.cjd, first ? s.ljar : s.ljd);
-        RS_ACC(3);
-        if (first) {
-            mat_vec(c, s.x, s.r, s.r);                         // r = M x0 - qfrc_smooth
-            RS_LANE_LOOP(k, s.ncon) {
-                // rows of the same geom pair at the previous evaluation's solution predict this evaluation's active rows
-                int bits = 16;
-                const int key = s.ckey(k);
-                for (int q = 0; q < s.nprev; q++) if ((s.cprev[q] >> 4) == key) bits = s.cprev[q] & 15;
-                int sign = 0;
-                RS_UNROLL1
-                for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
-                s.set_cact(k, bits < 16 ? bits : sign);
-            }
-            RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
-            if (RS_LANE0) s.lmask = s.pmask & s.pvalid;
-            RS_SYNC();
-            RS_LANE_LOOP(j, S::NU) { if (s.ljar[j] < 0.f && !((s.pvalid >> j) & 1)) RS_ATOMIC_OR(&s.lmask, 1 << j); }
-            RS_SYNC();
-            continue;
-        }
-        // does the active set survive the full step?
-        if (RS_LANE0) s.same = 1;
+    RS_ACC(5);
+    // residual pass: rows of J (x0 + B v), see make_constraints (s.d is free until the first Newton direction)
+    const float Bc = solref_damping(c.h);
+    RS_LANE_LOOP(i, S::NV) { s.d[i] = s.x[i] + Bc * s.v[i]; }
+    RS_SYNC();
+    twists(c, s.d);
+    rows_of(c, s.d, s.cjar, s.ljar);
+    RS_ACC(3);
+    mat_vec(c, s.x, s.r, s.r);                         // r = M x0 - qfrc_smooth
+    RS_LANE_LOOP(k, s.ncon) {
+        // rows of the same geom pair at the previous evaluation's solution predict this evaluation's active rows
+        int bits = 16;
+        const int key = s.ckey(k);
+        for (int q = 0; q < s.nprev; q++) if ((s.cprev[q] >> 4) == key) bits = s.cprev[q] & 15;
+        int sign = 0;
+        RS_UNROLL1
+        for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
+        s.set_cact(k, bits < 16 ? bits : sign);
+    }
+    RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
+    if (RS_LANE0) s.lmask = s.pmask & s.pvalid;
+    RS_SYNC();
+    RS_LANE_LOOP(j, S::NU) { if (s.ljar[j] < 0.f && !((s.pvalid >> j) & 1)) RS_ATOMIC_OR(&s.lmask, 1 << j); }
+    RS_SYNC();
+}
+
+// one Newton iteration from the current point (s.x, residuals s.r / s.cjar / s.ljar, active sets); true = converged
+template <int LA, int LB>
+RS_HD bool solve_iter(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_ACC(5);
+    // coupling that matters for THIS iteration's H: only contacts with active rows contribute J^T D J, so an inter- or
+    // intra-agent contact that is inside the margin but not loaded does not force the dense paths
+    if (RS_LANE0) s.coupled = 0;
+    RS_SYNC();
+    RS_LANE_LOOP(k, s.ncon) {
+        const int bA = s.bA(k), bB = s.bB(k);
+        if (bA >= 0 && s.cact(k) != 0)
+            RS_ATOMIC_OR(&s.coupled, ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1 : 2);
+    }
+    RS_SYNC();
+    jt_forces(c);
+    RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
+    RS_SYNC();
+    RS_ACC(0);
+    if (RS_ARROW && s.coupled == 0) build_H_arrow(c); else build_H(c);
+    RS_ACC(1);
+    if (RS_ARROW && s.coupled == 0) arrow_solve(c); else chol_solve(c);      // s.d = -H^-1 grad
+    RS_ACC(2);
+    twists(c, s.d);
+    rows_of(c, s.d, s.cjd, s.ljd);
+    RS_ACC(3);
+    // does the active set survive the full step?
+    if (RS_LANE0) s.same = 1;
+    RS_SYNC();
+    RS_LANE_LOOP(k, s.ncon) {
+        const int act = s.cact(k);
+        for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] + s.cjd[k][r] < 0.f)) s.same = 0;
+    }
+    RS_LANE_LOOP(j, S::NU) {
+        if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
+    }
+    RS_SYNC();
+    const int same = s.same;
+    int predicted = 0;
+    if (!same) {
+        // the full step leaves the active set: the iteration goes on from x + alpha d and needs M d (for r and the line search).
+        // Was the set used for this iteration the sign set at the current point?  (not when it came from the prediction)
+        if (RS_LANE0) s.pvalid = 0;
         RS_SYNC();
+        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] < 0.f))) s.pvalid = 1; }
         RS_LANE_LOOP(k, s.ncon) {
             const int act = s.cact(k);
-            for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] + s.cjd[k][r] < 0.f)) s.same = 0;
-        }
-        RS_LANE_LOOP(j, S::NU) {
-            if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] + s.ljd[j] < 0.f))) s.same = 0;
+            for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] < 0.f)) s.pvalid = 1;
         }
         RS_SYNC();
-        const int same = s.same;
-        int predicted = 0;
-        if (!same) {
-            // the full step leaves the active set: the iteration goes on from x + alpha d and needs M d (for r and the line search).
-            // Was the set used for this iteration the sign set at the current point?  (not when it came from the prediction)
-            if (RS_LANE0) s.pvalid = 0;
-            RS_SYNC();
-            RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && ((((s.lmask >> j) & 1) != 0) != (s.ljar[j] < 0.f))) s.pvalid = 1; }
-            RS_LANE_LOOP(k, s.ncon) {
-                const int act = s.cact(k);
-                for (int r = 0; r < 4; r++) if ((((act >> r) & 1) != 0) != (s.cjar[k][r] < 0.f)) s.pvalid = 1;
-            }
-            RS_SYNC();
-            predicted = s.pvalid;
-            mat_vec(c, s.d, s.Md, (const float*)0);
-        }
-        float alpha = 1.f;
-        if (!same && !predicted) {
-            // exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton inside a bracket
-            const float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
-            float lo = 0.f, hi = 0.f, d1, d2;
-            bool bracketed = false;
-            RS_UNROLL1
-            for (int k = 0; k < 20; k++) {
-                dphi(c, alpha, p0, p1, &d1, &d2);
-                if (d1 < 0.f) lo = alpha; else { hi = alpha; bracketed = true; }
-                if (!bracketed) { if (alpha >= 256.f) break; alpha *= 2.f; continue; }
-                if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
-                float an = alpha - RS_DIV(d1, d2);
-                if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
-                alpha = an;
-            }
-        }
-        if (same) { RS_LANE_LOOP(i, S::NV) { s.x[i] += s.d[i]; } }       // converged: r is not needed any more, M d was never formed
-        else { RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; } }
-        RS_LANE_LOOP(k, s.ncon) {
-            int sign = 0;
-            for (int r = 0; r < 4; r++) { s.cjar[k][r] += alpha * s.cjd[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
-            s.set_cact(k, sign);             // sign set at the new point
-        }
-        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
-        if (RS_LANE0) s.lmask = 0;
-        RS_SYNC();
-        RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.lmask, 1 << j); }     // sign set at the new point
-        RS_SYNC();
-        RS_ACC(4);
-        it++;
-        if (same) conv = true;
+        predicted = s.pvalid;
+        mat_vec(c, s.d, s.Md, (const float*)0);
     }
+    float alpha = 1.f;
+    if (!same && !predicted) {
+        // exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton inside a bracket
+        const float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
+        float lo = 0.f, hi = 0.f, d1, d2;
+        bool bracketed = false;
+        RS_UNROLL1
+        for (int k = 0; k < 20; k++) {
+            dphi(c, alpha, p0, p1, &d1, &d2);
+            if (d1 < 0.f) lo = alpha; else { hi = alpha; bracketed = true; }
+            if (!bracketed) { if (alpha >= 256.f) break; alpha *= 2.f; continue; }
+            if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
+            float an = alpha - RS_DIV(d1, d2);
+            if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
+            alpha = an;
+        }
+    }
+    if (same) { RS_LANE_LOOP(i, S::NV) { s.x[i] += s.d[i]; } }       // converged: r is not needed any more, M d was never formed
+    else { RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; } }
+    RS_LANE_LOOP(k, s.ncon) {
+        int sign = 0;
+        for (int r = 0; r < 4; r++) { s.cjar[k][r] += alpha * s.cjd[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
+        s.set_cact(k, sign);             // sign set at the new point
+    }
+    RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
+    if (RS_LANE0) s.lmask = 0;
+    RS_SYNC();
+    RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.lmask, 1 << j); }     // sign set at the new point
+    RS_SYNC();
+    RS_ACC(4);
+    return same != 0;
+}
+
+// the active sets at the solution become the next evaluation's prediction; diagnostics
+template <int LA, int LB>
+RS_HD void solve_finish(Ctx<LA, LB>& c, int it, bool conv) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
     RS_SOLVE_TRACE(s, it);
     RS_LANE_LOOP(k, s.ncon) { s.cprev[k] = (unsigned short)((s.ckey(k) << 4) | s.cact(k)); }
     if (RS_LANE0) s.nprev = s.ncon;
     if (RS_LANE0) { s.niter = it; s.tot_iter += it; s.tot_coupled += s.coupled & 1; s.tot_ncon += s.ncon; if (it > s.max_iter) s.max_iter = it; if (!conv) s.status |= RS_STATUS_NEWTON_MAXIT; }
     RS_SYNC();
+}
+
+template <int LA, int LB>
+RS_HD void solve(Ctx<LA, LB>& c) {
+    solve_first(c);
+    bool conv = false;
+    int it = 0;
+    while (!conv && it < c.max_newton) { conv = solve_iter(c); it++; }
+    solve_finish(c, it, conv);
 }
 
 // one forward evaluation: qacc(q, v) into s.x
@@ -1305,26 +1313,27 @@ RS_HD void solve(Ctx<LA, LB>& c) {
 #ifndef RS_SUBSTEP_SYNC
 #define RS_SUBSTEP_SYNC()
 #endif
-#ifndef RS_SOLVE_SYNC
-#define RS_SOLVE_SYNC()
-#endif
+// everything of a forward evaluation in front of the Newton iterations
 template <int LA, int LB>
-RS_HD void forward(Ctx<LA, LB>& c) {
-    RS_EVAL_SYNC();     // optional block-wide re-alignment of the warps (instruction-cache locality)
+RS_HD void eval_begin(Ctx<LA, LB>& c) {
     RS_CLOCK_BEGIN();
     fk(c);
-    RS_PHASE_SYNC();
     dynamics(c);
-    RS_PHASE_SYNC();
     RS_CLOCK_MARK(0);
     collide(c);
     RS_CLOCK_MARK(1);
-    RS_PHASE_SYNC();
     make_constraints(c);
-    RS_PHASE_SYNC();
-    RS_SOLVE_SYNC();
     RS_CLOCK_MARK(2);
-    solve(c);
+    solve_first(c);
+}
+template <int LA, int LB>
+RS_HD void forward(Ctx<LA, LB>& c) {
+    RS_EVAL_SYNC();     // optional block-wide re-alignment of the warps (instruction-cache locality)
+    eval_begin(c);
+    bool conv = false;
+    int it = 0;
+    while (!conv && it < c.max_newton) { conv = solve_iter(c); it++; }
+    solve_finish(c, it, conv);
     RS_CLOCK_MARK(3);
     RS_CLOCK_END();
 }
@@ -1358,35 +1367,83 @@ RS_HD void integrate_pos(Ctx<LA, LB>& c, const float* vel, float dt) {
 }
 
 // do_simulation: nsub x mj_step with RK4 (mujoco_env.py:125-129; mj_RungeKutta N=4)
+// RK4 bookkeeping after the evaluation of stage `st` (0..3) of a substep: accumulate, move to the next stage's state or finish the substep
 template <int LA, int LB>
-RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
+RS_HD void rk_after_eval(Ctx<LA, LB>& c, int st) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
     const float h = c.h;
-    for (int sub = 0; sub < nsub; sub++) {
-        RS_SUBSTEP_SYNC();
-        RS_LANE_LOOP(i, S::NQ) { s.q0[i] = s.q[i]; }
-        RS_LANE_LOOP(i, S::NV) { s.v0[i] = s.v[i]; s.vsum[i] = 0.f; s.asum[i] = 0.f; }
+    if (st == 0) {   // mj_forward normalised qpos in place: carry that into the substep origin
+        RS_LANE_LOOP(a, 2) { for (int k = 3; k < 7; k++) s.q0[c.qadr(a) + k] = s.q[c.qadr(a) + k]; }
+    }
+    const float B = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
+    const float A = (st == 2) ? 1.f : 0.5f;
+    RS_LANE_LOOP(i, S::NV) { s.vsum[i] += B * s.v[i]; s.asum[i] += B * s.x[i]; }
+    RS_SYNC();
+    if (st < 3) {
+        integrate_pos(c, s.v, h * A);
+        RS_LANE_LOOP(i, S::NV) { s.v[i] = s.v0[i] + h * A * s.x[i]; }
         RS_SYNC();
-        for (int st = 0; st < 4; st++) {
-            forward(c);
-            if (st == 0) {   // mj_forward normalised qpos in place: carry that into the substep origin
-                RS_LANE_LOOP(a, 2) { for (int k = 3; k < 7; k++) s.q0[c.qadr(a) + k] = s.q[c.qadr(a) + k]; }
-            }
-            const float B = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
-            const float A = (st == 2) ? 1.f : 0.5f;
-            RS_LANE_LOOP(i, S::NV) { s.vsum[i] += B * s.v[i]; s.asum[i] += B * s.x[i]; }
-            RS_SYNC();
-            if (st < 3) {
-                integrate_pos(c, s.v, h * A);
-                RS_LANE_LOOP(i, S::NV) { s.v[i] = s.v0[i] + h * A * s.x[i]; }
-                RS_SYNC();
-            }
-        }
+    } else {
         integrate_pos(c, s.vsum, h);
         RS_LANE_LOOP(i, S::NV) { s.v[i] = s.v0[i] + h * s.asum[i]; }
         RS_SYNC();
     }
+}
+template <int LA, int LB>
+RS_HD void substep_begin(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    RS_LANE_LOOP(i, S::NQ) { s.q0[i] = s.q[i]; }
+    RS_LANE_LOOP(i, S::NV) { s.v0[i] = s.v[i]; s.vsum[i] = 0.f; s.asum[i] = 0.f; }
+    RS_SYNC();
+}
+
+#ifndef RS_TRIP_ANY
+#define RS_TRIP_ANY(p) (p)      // device: __syncthreads_or -- the block-wide vote doubles as the barrier that re-aligns the warps
+#define RS_TRIP_SYNC()
+#endif
+#ifndef RS_TRIP_MACHINE
+#define RS_TRIP_MACHINE 1
+#endif
+// The warps of a block must run the same code at the same time (the kernel is several times the SM's instruction cache), but the
+// pairs need different numbers of Newton iterations per evaluation (1 for 70 %, 2 for 25 %, 3..6 for the rest).  Re-aligning once
+// per EVALUATION made every block wait for its slowest pair twenty times per step (the 46 % barrier stall of round 1).  Here the
+// block re-aligns once per TRIP = [start of an evaluation, for the warps that begin one] + [one Newton iteration, every warp]:
+// a pair that needs an extra iteration simply starts its next evaluation one trip later, nobody waits for its whole tail, and a
+// block is finished after max-over-pairs(total iterations of the step) trips instead of sum-over-evaluations(max-over-pairs).
+template <int LA, int LB>
+RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
+#if RS_TRIP_MACHINE
+    int sub = 0, st = 0, it = 0;
+    bool fresh = true, done = nsub <= 0;
+    if (!done) substep_begin(c);
+    while (RS_TRIP_ANY(!done)) {
+        if (!done && fresh) { eval_begin(c); it = 0; fresh = false; }
+        RS_TRIP_SYNC();
+        if (!done) {
+            const bool conv = solve_iter(c);
+            it++;
+            if (conv || it >= c.max_newton) {
+                solve_finish(c, it, conv);
+                RS_CLOCK_MARK(3);
+                RS_CLOCK_END();
+                rk_after_eval(c, st);
+                fresh = true;
+                if (++st == 4) { st = 0; if (++sub == nsub) done = true; else substep_begin(c); }
+            }
+        }
+    }
+#else
+    for (int sub = 0; sub < nsub; sub++) {
+        RS_SUBSTEP_SYNC();
+        substep_begin(c);
+        for (int st = 0; st < 4; st++) {
+            forward(c);
+            rk_after_eval(c, st);
+        }
+    }
+#endif
 }
 
 }  // namespace rs

@@ -63,6 +63,15 @@ for rep in range(NS):
             print('   %s evals: n %d, solve cycles by iterations: ' % (lab, m.sum()) +
                   ', '.join('%d it: %.0f (n=%d)' % (k, e_sol[m][its == k].mean(), (its == k).sum()) for k in range(1, 7) if (its == k).any()) +
                   ' | pre-solve %.0f' % e_pre[m].mean())
+    for its_k in (1, 2, 3):
+        m = (cpl == 0) & (nit == its_k)
+        print('   uncoupled evals with %d iteration(s), solve cycles by contact count: ' % its_k +
+              ', '.join('%d:%.0f(n=%d)' % (k, e_sol[m & (ncon == k)].mean(), (m & (ncon == k)).sum()) for k in range(0, 13) if (m & (ncon == k)).sum() > 3))
+    m = (cpl == 1) & (nit == 1)
+    print('   coupled evals with 1 iteration, solve cycles by contact count: ' +
+          ', '.join('%d:%.0f(n=%d)' % (k, e_sol[m & (ncon == k)].mean(), (m & (ncon == k)).sum()) for k in range(0, 16) if (m & (ncon == k)).sum() > 1))
+    print('   pre-solve cycles by contact count: ' + ', '.join('%d:%.0f' % (k, e_pre[ncon == k].mean()) for k in range(0, 13) if (ncon == k).sum() > 3))
+    print('   contact count histogram (all evals): ' + str(np.bincount(ncon.ravel(), minlength=12)[:16].tolist()))
     rows.append((busy.mean(), span.max()))
 print('mean over steps: pair busy %.0f cycles, slowest block span %.0f cycles' % (np.mean([r[0] for r in rows]), np.mean([r[1] for r in rows])))
 
