@@ -27,11 +27,10 @@ __device__ __forceinline__ long long rs_clock() { long long t; asm volatile("mov
 #if defined(__CUDA_ARCH__)
 #if RS_SYNC_MODE == 7
 #define RS_TRIP_ANY(p) __syncthreads_or(p)
-#ifndef RS_TRIP_NO_MID
 #define RS_TRIP_SYNC() __syncthreads()
 #endif
-#elif RS_SYNC_MODE == 1
-#define RS_EVAL_SYNC() __syncthreads()
+#if RS_SYNC_MODE != 0
+#define RS_EVAL_SYNC() __syncthreads()      // forward(): the per-evaluation path (six- and eight-legged bodies, rs_forward_debug)
 #endif
 #ifdef RS_EXPERIMENT_CLOCK
 #define RS_ACC(i) { __syncwarp(); long long rs_now = rs_clock(); c.acc[i] += rs_now - c.tlast; c.tlast = rs_now; }
@@ -284,6 +283,8 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_forward_debug(EnvDev d, const f
 // morphology pairs: legs per agent in {4 (ant), 6 (bug), 8 (spider)}, all nine combinations (robosumo/__init__.py:8-105)
 #ifdef RS_DEV_ANT_ONLY      /* developer builds: only Ant-vs-Ant (the full build takes ~85 s) */
 #define RS_FOR_PAIRS(X) X(4, 4)
+#elif defined(RS_DEV_SAME_ONLY) /* developer builds: the three same-morphology pairs */
+#define RS_FOR_PAIRS(X) X(4, 4) X(6, 6) X(8, 8)
 #else
 #define RS_FOR_PAIRS(X) X(4, 4) X(4, 6) X(4, 8) X(6, 4) X(6, 6) X(6, 8) X(8, 4) X(8, 6) X(8, 8)
 #endif

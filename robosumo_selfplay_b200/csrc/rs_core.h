@@ -1004,6 +1004,43 @@ RS_HD void arrow_solve(Ctx<LA, LB>& c) {
         H[AR::Y0 + 2 * g] = i00 * gh + i01 * ga; H[AR::Y0 + 2 * g + 1] = i01 * gh + i11 * ga;
     }
     RS_SYNC();
+#if defined(__CUDA_ARCH__) && !defined(RS_NO_REG_GJ)
+    // Schur complement onto the two floating bases and its 6x6 elimination with the rows in registers: lane 6 a + r owns row r
+    // of agent a (7 numbers), the pivot row travels by warp shuffle -- no shared-memory round trip and no barrier per pivot
+    {
+        const int lane = threadIdx.x & 31, a = lane >= 6 ? 1 : 0, r = lane - 6 * a;
+        const bool own = lane < 12;
+        float row[7];
+#pragma unroll
+        for (int cc = 0; cc < 7; cc++) row[cc] = 0.f;
+        if (own) {
+            const int l0 = c.leg0(a), va = c.vadr(a);
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++) row[cc] = H[AR::A0 + a * 36 + r * 6 + cc];
+            row[6] = -s.d[va + r];
+            RS_UNROLL1
+            for (int l = 0; l < c.L(a); l++) {
+                const float* W = H + AR::W0 + 12 * (l0 + l); const float* B = H + AR::B0 + 12 * (l0 + l); const float* Y = H + AR::Y0 + 2 * (l0 + l);
+                const float w0 = W[2 * r], w1 = W[2 * r + 1];
+#pragma unroll
+                for (int cc = 0; cc < 6; cc++) row[cc] -= w0 * B[2 * cc] + w1 * B[2 * cc + 1];
+                row[6] -= B[2 * r] * Y[0] + B[2 * r + 1] * Y[1];
+            }
+        }
+        float diag = 1.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int src = own ? 6 * a + k : lane;
+            const float pk = __shfl_sync(0xffffffffu, row[k], src);
+            const float f = (r == k) ? 0.f : row[k] * RS_RCP(fmaxf(pk, 1e-12f));
+            if (r == k) diag = pk;
+#pragma unroll
+            for (int cc = k + 1; cc < 7; cc++) row[cc] = fmaf(-f, __shfl_sync(0xffffffffu, row[cc], src), row[cc]);
+        }
+        if (own) s.d[c.vadr(a) + r] = row[6] * RS_RCP(fmaxf(diag, 1e-12f));
+    }
+    RS_SYNC();
+#else
     // Schur complement onto the floating base, upper triangle + right-hand side (27 entries per agent), mirrored
     RS_LANE_LOOP(e, 54) {
         const int a = e >= 27 ? 1 : 0, t = e - 27 * a;
@@ -1051,11 +1088,12 @@ RS_HD void arrow_solve(Ctx<LA, LB>& c) {
         row[6] = v; s.d[c.vadr(a) + jr] = v;
     }
     RS_SYNC();
+#endif
     RS_LANE_LOOP(g, S::LT) {
         const int a = c.agent_of_leg(g), dh = c.hipdof(g);
-        const float* W = H + AR::W0 + 12 * g; const float* St = H + AR::S0 + a * 42;
+        const float* W = H + AR::W0 + 12 * g;
         float dh_ = H[AR::Y0 + 2 * g], da_ = H[AR::Y0 + 2 * g + 1];
-        for (int k = 0; k < 6; k++) { const float dt = St[k * 7 + 6]; dh_ -= W[2 * k] * dt; da_ -= W[2 * k + 1] * dt; }
+        for (int k = 0; k < 6; k++) { const float dt = s.d[c.vadr(a) + k]; dh_ -= W[2 * k] * dt; da_ -= W[2 * k + 1] * dt; }
         s.d[dh] = dh_; s.d[dh + 1] = da_;
     }
     RS_SYNC();
@@ -1139,13 +1177,66 @@ RS_HD void dphi(Ctx<LA, LB>& c, float alpha, float p0, float p1, float* d1, floa
 #endif
 }
 
+// p0 = d . r and p1 = d . (M d) of the line search (uniform result)
 template <int LA, int LB>
-RS_HD float dot_nv(Ctx<LA, LB>& c, const float* a, const float* b) {
+RS_HD void ls_dots(Ctx<LA, LB>& c, float* p0, float* p1) {
     typedef Slab<LA, LB> S;
-    float acc = 0.f;
+    S& s = *c.s;
+    float a = 0.f, b = 0.f;
+    RS_LANE_LOOP(i, S::NV) { a += s.d[i] * s.r[i]; b += s.d[i] * s.Md[i]; }
+#if defined(__CUDA_ARCH__)
     RS_UNROLL1
-    for (int i = 0; i < S::NV; i++) acc += a[i] * b[i];
-    return acc;
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+#endif
+    *p0 = a; *p1 = b;
+}
+// row i of the line search: contact rows first (4 per contact), then the limit rows; false = the row does not exist
+template <int LA, int LB>
+RS_HD bool ls_row(const Slab<LA, LB>& s, int i, int nc4, float* jar, float* jd, float* D) {
+    typedef Slab<LA, LB> S;
+    if (i < nc4) { *jar = (&s.cjar[0][0])[i]; *jd = (&s.cjd[0][0])[i]; *D = s.cD[i >> 2]; return true; }
+    const int j = i - nc4;
+    *jar = s.ljar[j]; *jd = s.ljd[j]; *D = s.lD[j];
+    return s.lsgn[j] != 0.f;
+}
+// Exact line search along s.d: phi'(alpha) = p0 + alpha p1 + sum_rows D (jar + alpha jd) jd [jar + alpha jd < 0] is increasing and
+// piecewise linear with one breakpoint -jar / jd per row.  Every lane takes breakpoints and evaluates phi' there (a loop over the
+// rows; the row data are warp-uniform shared-memory reads), the warp keeps the largest breakpoint with phi' < 0 and the smallest
+// with phi' >= 0, and one Newton step from the middle of that linear piece lands on the root: one pass instead of the up to 20
+// bracketing / safeguarded-Newton evaluations (each a warp reduction) of round 1.
+template <int LA, int LB>
+RS_HD float line_search(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    float p0, p1;
+    ls_dots(c, &p0, &p1);
+    const int nc4 = 4 * s.ncon, R = nc4 + S::NU;
+    float lo = 0.f, hi = 3.0e38f;
+    RS_LANE_LOOP(i, R) {
+        float jar, jd, D;
+        if (!ls_row(s, i, nc4, &jar, &jd, &D) || jd == 0.f) continue;
+        const float a = -RS_DIV(jar, jd);
+        if (!(a > 0.f && a < 1.0e30f)) continue;
+        float acc = p0 + a * p1;
+        RS_UNROLL1
+        for (int r = 0; r < R; r++) {
+            float jr, jdr, Dr;
+            if (!ls_row(s, r, nc4, &jr, &jdr, &Dr)) continue;
+            const float j = jr + a * jdr;
+            if (j < 0.f) acc += Dr * j * jdr;
+        }
+        if (acc < 0.f) lo = fmaxf(lo, a); else hi = fminf(hi, a);
+    }
+#if defined(__CUDA_ARCH__)
+    RS_UNROLL1
+    for (int o = 16; o; o >>= 1) { lo = fmaxf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fminf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+#endif
+    const float am = hi < 1.0e38f ? 0.5f * (lo + hi) : 2.f * fmaxf(lo, 0.5f);      // inside the linear piece that holds the root
+    float d1, d2;
+    dphi(c, am, p0, p1, &d1, &d2);
+    float alpha = am - RS_DIV(d1, d2);
+    alpha = fminf(fmaxf(alpha, lo), hi);
+    return alpha;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1248,22 +1339,7 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
         mat_vec(c, s.d, s.Md, (const float*)0);
     }
     float alpha = 1.f;
-    if (!same && !predicted) {
-        // exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton inside a bracket
-        const float p0 = dot_nv(c, s.d, s.r), p1 = dot_nv(c, s.d, s.Md);
-        float lo = 0.f, hi = 0.f, d1, d2;
-        bool bracketed = false;
-        RS_UNROLL1
-        for (int k = 0; k < 20; k++) {
-            dphi(c, alpha, p0, p1, &d1, &d2);
-            if (d1 < 0.f) lo = alpha; else { hi = alpha; bracketed = true; }
-            if (!bracketed) { if (alpha >= 256.f) break; alpha *= 2.f; continue; }
-            if (fabsf(d1) <= 1e-6f * fabsf(p0) || hi - lo < 1e-7f * hi) break;
-            float an = alpha - RS_DIV(d1, d2);
-            if (!(an > lo && an < hi)) an = 0.5f * (lo + hi);
-            alpha = an;
-        }
-    }
+    if (!same && !predicted) alpha = line_search(c);
     if (same) { RS_LANE_LOOP(i, S::NV) { s.x[i] += s.d[i]; } }       // converged: r is not needed any more, M d was never formed
     else { RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; } }
     RS_LANE_LOOP(k, s.ncon) {
@@ -1404,7 +1480,7 @@ RS_HD void substep_begin(Ctx<LA, LB>& c) {
 #define RS_TRIP_SYNC()
 #endif
 #ifndef RS_TRIP_MACHINE
-#define RS_TRIP_MACHINE 1
+#define RS_TRIP_MACHINE 1      // 0: re-align per evaluation for every morphology (round-1 behaviour)
 #endif
 // The warps of a block must run the same code at the same time (the kernel is several times the SM's instruction cache), but the
 // pairs need different numbers of Newton iterations per evaluation (1 for 70 %, 2 for 25 %, 3..6 for the rest).  Re-aligning once
@@ -1414,7 +1490,10 @@ RS_HD void substep_begin(Ctx<LA, LB>& c) {
 // block is finished after max-over-pairs(total iterations of the step) trips instead of sum-over-evaluations(max-over-pairs).
 template <int LA, int LB>
 RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
-#if RS_TRIP_MACHINE
+    // measured at E = 4096 (tools/bench_morphologies.py): Ant 1.65 -> 1.61 ms per trip, Bug 5.01 -> 5.06 (equal), Spider 7.56 -> 8.11:
+    // the larger bodies have 19 / 15 warps per block (bigger slabs) and less to gain from not waiting, so they keep the
+    // per-evaluation re-alignment
+    if constexpr (RS_TRIP_MACHINE && LA + LB <= 8) {
     int sub = 0, st = 0, it = 0;
     bool fresh = true, done = nsub <= 0;
     if (!done) substep_begin(c);
@@ -1434,7 +1513,7 @@ RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
             }
         }
     }
-#else
+    } else {
     for (int sub = 0; sub < nsub; sub++) {
         RS_SUBSTEP_SYNC();
         substep_begin(c);
@@ -1443,7 +1522,7 @@ RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
             rk_after_eval(c, st);
         }
     }
-#endif
+    }
 }
 
 }  // namespace rs
