@@ -98,11 +98,22 @@ class ClockSampler(threading.Thread):
                 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
+CPU_FLAGS = None
+
+
 def cpu_port_rate(seconds, envs, threads):
     """Oracle port (oracle/physics_oracle.c) stepping `envs` independent pairs with `threads` host threads for
-    about `seconds`; the env-level reward/obs arithmetic is negligible beside the physics and is not included."""
+    about `seconds`; the env-level reward/obs arithmetic is negligible beside the physics and is not included.
+    The library is compiled on THIS machine with -O3 -march=native before it is timed (oracle/Makefile `native`)."""
+    global CPU_FLAGS
     import numpy as np
+    from oracle import physics as op
     from oracle.physics import OracleModel, load_model_json
+    if CPU_FLAGS is None:
+        try:
+            CPU_FLAGS = op.use_native_build()
+        except AssertionError:                     # already loaded (smoke / tests in the same process): report what is loaded
+            CPU_FLAGS = op.NATIVE_FLAGS if op._NATIVE else op.PORTABLE_FLAGS
     om = OracleModel(load_model_json('ant_ant'))
     rng = np.random.RandomState(0)
     q = np.tile(om.qpos0, (envs, 1)); v = np.zeros((envs, om.nv)); w = np.zeros((envs, om.nv))
@@ -164,7 +175,7 @@ def run_reference(args, rank, world):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'RoboSumo-Ant-vs-Ant-v0 physics step, CPU oracle port on host cores',
                    'envs_per_step': envs, 'frame_skip': 5, 'integrator': 'RK4'},
-        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'compiler_flags': 'gcc ' + str(CPU_FLAGS),
                          'sample': '%d env pairs x ~%.1f s per step, %d steps, N(0,1) actions' % (envs, per_step_s, args.steps)},
         'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -181,7 +192,7 @@ def measure_learner(args, E, local, rank, world, dev):
     from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
     from robosumo_selfplay_b200.model import PPOModel
     from robosumo_selfplay_b200.runner import Runner
-    from robosumo_selfplay_b200.dist import Comm, split_minibatch, EpochPermutations
+    from robosumo_selfplay_b200.dist import Comm, EpochSchedule, EpochPermutations
     from robosumo_selfplay_b200 import _lib
     T, nmb, nep = args.nsteps, 32, 6
     comm = Comm() if world > 1 else None
@@ -211,19 +222,18 @@ def measure_learner(args, E, local, rank, world, dev):
     nbt = N // nmb
     lo, hi = rank * N_local, (rank + 1) * N_local
     model = models[0]
+    sched = EpochSchedule(dev, N, nbt, lo, hi, comm)
+    l0 = _lib.lib().rs_launch_count()
     def one_update(perms=None):
-        for inds in (perms if perms is not None else EpochPermutations(N, nep)):     # the reference's per-epoch np.random.shuffle, replayed bit-exactly one epoch ahead
-            if world == 1:
-                di = torch.as_tensor(inds.astype(np.int32), device=dev)
-                parts = [di[s0:s0 + nbt] for s0 in range(0, N, nbt)]
-            else:
-                loc = [split_minibatch(inds[s0:s0 + nbt], lo, hi) for s0 in range(0, N, nbt)]
-                cat = torch.as_tensor(np.concatenate(loc), device=dev); offs = np.cumsum([0] + [len(x) for x in loc])
-                parts = [cat[offs[i]:offs[i + 1]] for i in range(len(loc))]
-            for mb in parts:
-                model.train_indexed(1e-3, 0.2, data['obs'], data['returns'], data['actions'], data['values'], data['neglogpacs'], None, mb, global_n=nbt)
+        # the reference's per-epoch np.random.shuffle, replayed bit-exactly on the host (one epoch ahead on a helper thread); the
+        # permutation goes to the device once per epoch, where the minibatches are split by rank and their advantage moments computed
+        for inds in (perms if perms is not None else EpochPermutations(N, nep, dtype=np.int32)):
+            for mb, n_loc, gn, sums in sched.load(inds, data['returns'], data['values']):
+                model.train_indexed(1e-3, 0.2, data['obs'], data['returns'], data['actions'], data['values'], data['neglogpacs'], None, mb,
+                                    global_n=gn, adv_sums=sums)
     one_update()                                        # warm-up
     torch.cuda.synchronize()
+    upd_launches = _lib.lib().rs_launch_count() - l0
     if comm is not None:
         comm.barrier()
     t0 = time.perf_counter()
@@ -232,27 +242,121 @@ def measure_learner(args, E, local, rank, world, dev):
     upd_s = time.perf_counter() - t0
     # the same update the way alg_ppo.learn runs it: the six permutations depend on the generator stream only and are drawn on the
     # helper thread WHILE the rollout runs, so inside the training loop the update does not wait for them
-    perms = EpochPermutations(N, nep, ahead=nep)
+    perms = EpochPermutations(N, nep, ahead=nep, dtype=np.int32)
     runner.run(1, as_numpy=False)
     torch.cuda.synchronize()
     if comm is not None:
         comm.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    e0.record()
     one_update(perms)
+    e1.record()
     torch.cuda.synchronize()
     upd_loop_s = time.perf_counter() - t0
-    tt = torch.tensor([roll_s, upd_s, upd_loop_s], dtype=torch.float64, device=dev)
+    upd_gpu_s = e0.elapsed_time(e1) / 1e3
+    tt = torch.tensor([roll_s, upd_s, upd_loop_s, upd_gpu_s], dtype=torch.float64, device=dev)
     if comm is not None:
-        comm.all_reduce_sum(tt); tt /= world
-    roll_s, upd_s, upd_loop_s = float(tt[0]), float(tt[1]), float(tt[2])
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)          # max over ranks
+    roll_s, upd_s, upd_loop_s, upd_gpu_s = [float(x) for x in tt]
     flops = 114.6e3 * N * nep
+    env.close()
     return {'rollout': {'value': E * world * T / roll_s, 'unit': 'env-steps/s', 'T': T, 'launches_per_step': roll_launches / T,
                         'rollout_seconds': roll_times, 'note': 'Runner.run -> rs_rollout: T steps behind one library call; per step 1 MLP launch (4 policy evaluations, tcgen05 tf32), 1 sampling launch, 1 physics launch and 2 trajectory-write launches, no host work in between; median of 3 rollouts'},
-            'ppo_update': {'value': upd_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
-                           'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_s / 1e12,
-                           'achieved_gbs': 536.0 * N * nep / upd_s / 1e9,
-                           'in_training_loop': {'value': upd_loop_s, 'unit': 's/iter', 'note': 'permutations drawn by the helper thread during the preceding rollout, as alg_ppo.learn does'},
-                           'note': 'stand-alone update: wall clock incl. the host-side replay of the six legacy NumPy shuffles (bit-exact schedule; one epoch ahead of the GPU) and the gradient all-reduce when N > 1'}}
+            'ppo_update': {'value': upd_loop_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
+                           'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_loop_s / 1e12,
+                           'achieved_gbs': 536.0 * N * nep / upd_loop_s / 1e9, 'launches_per_minibatch': upd_launches / float(nmb * nep),
+                           'gpu_seconds': upd_gpu_s,
+                           'standalone': {'value': upd_s, 'unit': 's/iter', 'note': 'same update started cold: includes the host-side replay of the six legacy NumPy shuffles over all %d GLOBAL indices (bit-exact schedule, one epoch ahead of the GPU) on the critical path' % N},
+                           'note': 'as alg_ppo.learn runs it (max over ranks): V-trace is part of the rollout; the six permutations are drawn by the helper thread during the preceding rollout; per epoch one H2D of the int32 permutation, one device-side split + advantage-moment launch (one all-reduce per epoch when N > 1), per minibatch 3 launches and ONE gradient all-reduce'}}
+
+
+def measure_config1_ref_shape(local, dev):
+    """BASELINE.json configs[0]: the reference's own shape -- 8 envs, nsteps = 2048 (learn()'s default) / 8192 (defaults.py:9),
+    32 minibatches x 6 epochs (defaults.py:8-26).  Rollout env-steps/s and update s/iter on ONE GPU."""
+    import numpy as np
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200.runner import Runner
+    from robosumo_selfplay_b200.dist import EpochPermutations, EpochSchedule
+    E, T, nmb, nep = 8, 2048, 32, 6
+    np.random.seed(1)
+    env = B200SumoVecEnv(ENV_ID, num_envs=E, seed=5, device=local, device_api=True)
+    models = [PPOModel(ob_dim=121, ac_dim=8, device=local), PPOModel(ob_dim=121, ac_dim=8, trainable=False, device=local)]
+    runner = Runner(env=env, models=models, nsteps=64, gamma=0.995, lam=1.0, rho_bar=10.0, c_bar=1.0, anneal_bound=1000)
+    runner.run(1, as_numpy=False)
+    runner.nsteps = T
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    R = runner.run(1, as_numpy=False)
+    torch.cuda.synchronize(); roll_s = time.perf_counter() - t0
+    out = {'envs': E, 'rollout': {'T': T, 'value': E * T / roll_s, 'unit': 'env-steps/s', 'seconds': roll_s,
+                                  'note': '8 pairs occupy 8 warps of 8 SMs: the step is bound by the dependent-instruction latency of one pair (~1 ms), not by throughput'}}
+    for Tu, rep in ((2048, 1), (8192, 4)):
+        data = {k: R[k][0].repeat(*([rep] + [1] * (R[k][0].dim() - 1))).contiguous() for k in ('obs', 'returns', 'actions', 'values', 'neglogpacs')}
+        N = E * Tu
+        sched = EpochSchedule(dev, N, N // nmb)
+        def upd():
+            for inds in EpochPermutations(N, nep, dtype=np.int32):
+                for mb, n_loc, gn, sums in sched.load(inds, data['returns'], data['values']):
+                    models[0].train_indexed(1e-3, 0.2, data['obs'], data['returns'], data['actions'], data['values'], data['neglogpacs'], None, mb, global_n=gn, adv_sums=sums)
+        upd(); torch.cuda.synchronize(); t0 = time.perf_counter(); upd(); torch.cuda.synchronize()
+        out['ppo_update_T%d' % Tu] = {'value': time.perf_counter() - t0, 'unit': 's/iter', 'samples': N, 'minibatch': N // nmb, 'nminibatches': nmb, 'noptepochs': nep,
+                                      'data': 'rollout of T=2048' + ('' if rep == 1 else ' tiled x%d to the T=8192 sample count' % rep)}
+    env.close()
+    return out
+
+
+def measure_config3_morphologies(local, dev, E):
+    """BASELINE.json configs[2]: Bug-vs-Bug and Spider-vs-Spider (more legs / contacts, intra-agent collisions), E pairs."""
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    out = {}
+    for name, A, bytes_ in (('Bug', 12, 2042), ('Spider', 16, 2554)):
+        env = B200SumoVecEnv('RoboSumo-%s-vs-%s-v0' % (name, name), num_envs=E, seed=3, device=local, device_api=True)
+        env.reset()
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        acts = [torch.randn(E, 2, A, device=dev, generator=g) for _ in range(8)]
+        for t in range(80):
+            env.step(acts[t % 8])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for t in range(30):
+            env.step(acts[t % 8])
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 30
+        bits, n = env.check_status(strict=False)
+        out[name.lower()] = {'envs': E, 'ms_per_step': ms, 'value': E / ms * 1e3, 'unit': 'env-steps/s', 'steps': 30, 'status_bits': bits,
+                             'roofline_hbm_frac': bytes_ * E / (ms / 1e3) / 1e9 / read_peaks()[0]}
+        env.close()
+    return out
+
+
+def measure_config5_eval(local, dev):
+    """BASELINE.json configs[4]: the evaluation loop of eval_robosumo_against_fix.py:198-243 -- 32 envs (adjust_z = -0.5), the
+    learner deterministic against a policy_zoo MLP (ant, tanh 64-64 with observation filter).  The reference asset
+    agent-params-v3.npy does not travel to the GPU box, so the zoo parameters are synthetic of the same layout (24 645 floats)."""
+    import numpy as np
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    from robosumo_selfplay_b200.model import PPOModel
+    from robosumo_selfplay_b200.policy_zoo import ZooMLPPolicy, evaluate_against_fixed
+    rng = np.random.RandomState(0)
+    n = 3 + 2 * 120 + 1 + 2 * (120 * 64 + 64 + 64 * 64 + 64) + 64 + 1 + 64 * 8 + 8 + 8
+    flat = (rng.randn(n) * 0.1).astype(np.float32)
+    flat[0:3] = [5.0, 80.0, 10.0]; flat[3:123] = rng.randn(120); flat[123:243] = 20 + rng.rand(120) * 30; flat[243] = 10.0
+    np.random.seed(2)
+    env = B200SumoVecEnv(ENV_ID, num_envs=32, seed=9, device=local, device_api=True, adjust_z=-0.5)
+    model = PPOModel(ob_dim=121, ac_dim=8, trainable=False, device=local)
+    zoo = ZooMLPPolicy(flat, 120, 8, device=local)
+    evaluate_against_fixed(env, model, zoo, rounds=8, max_steps=50)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = evaluate_against_fixed(env, model, zoo, rounds=10 ** 9, max_steps=600)
+    torch.cuda.synchronize(); el = time.perf_counter() - t0
+    env.close()
+    return {'envs': 32, 'steps': res['steps'], 'rounds': res['rounds'], 'value': 32 * res['steps'] / el, 'unit': 'env-steps/s', 'rounds_per_s': res['rounds'] / el,
+            'win': res['win'], 'draw': res['draw'], 'lose': res['lose'], 'opponent': 'policy_zoo MLP layout, synthetic parameters',
+            'note': 'per step: 2 MLP launches + 1 physics launch + the host-side win/draw/lose tally of the script (one D2H sync per step)'}
 
 
 def main():
@@ -343,10 +447,22 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = E * world * n_e2e / float(e2e_t.item())
+    # the same through the PYTHON drop-in a Runner / eval script calls: B200SumoVecEnv.step(numpy actions) -> (obs, rews, dones, infos)
+    # with float64 obs / rewards as SubprocVecEnv returns them and the lazily materialised infos
+    t0 = time.perf_counter()
+    for t in range(n_e2e):
+        o_, r_, d_, infos_ = henv.step(hact[t % 8])
+        _ = infos_[t % E][0]['shaping_reward']                # a consumer touching one entry
+    e2e_py_s = time.perf_counter() - t0
+    e2e_py_t = torch.tensor([e2e_py_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_py_t, op=dist.ReduceOp.MAX)
+    e2e_py_value = E * world * n_e2e / float(e2e_py_t.item())
     h2d = a32.nbytes
     d2h = henv.h_obs.nbytes + henv.h_rew.nbytes + henv.h_done.nbytes + henv.h_info.nbytes + henv.h_epi.nbytes
     learner = None
     config4 = None
+    extra_configs = None
     if not args.no_learner:
         # BASELINE.json configs[3]: 65 536 env pairs in total, sharded over the ranks (several waves of blocks per SM: the
         # per-block slowest-warp tail of a single wave averages out)
@@ -373,6 +489,9 @@ def main():
                    'value': E4 * world / (float(ms4.item()) / 1e3), 'unit': 'env-steps/s', 'steps': 20}
         env4.close(); del env4, pool4
         learner = measure_learner(args, E, local, rank, world, dev)
+        if rank == 0 and world == 1:
+            extra_configs = {'config1_ref_shape': measure_config1_ref_shape(local, dev), 'config3_morphologies': measure_config3_morphologies(local, dev, E),
+                             'config5_eval': measure_config5_eval(local, dev)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -417,10 +536,11 @@ def main():
                      'fp32': fp32,
                      'note': 'state stays in shared memory for all 20 forward evaluations; the kernel is FP32-latency/'
                              'issue bound by construction, so the HBM fraction is low (DESIGN.md)'},
-        'cpu_baseline': {'value': cpu_rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+        'cpu_baseline': {'value': cpu_rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'compiler_flags': 'gcc ' + str(CPU_FLAGS),
                          'sample': '%d env-steps (%d pairs, N(0,1) actions) in %.1f s on %d threads' % (cpu_n, 16 * cores, cpu_el, cores)},
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'steps': n_e2e, 'api': 'rs_step_host (B200SumoVecEnv host style: numpy actions in through pinned staging, obs/rew/done/info/episode copied straight into the page-locked numpy result buffers)'},
+                'steps': n_e2e, 'api': 'rs_step_host (B200SumoVecEnv host style: numpy actions in through pinned staging, obs/rew/done/info/episode copied straight into the page-locked numpy result buffers)',
+                'python_dropin': {'value': e2e_py_value, 'unit': 'env-steps/s', 'api': 'B200SumoVecEnv.step(numpy) -> float64 obs / rewards, bool dones, lazily materialised infos (what the reference Runner / eval scripts call)'}},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'contact_full_envs': ncon_note,
@@ -429,6 +549,8 @@ def main():
         line['learner'] = learner
     if config4 is not None:
         line['config4_65536_pairs'] = config4
+    if extra_configs is not None:
+        line.update(extra_configs)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -138,12 +138,27 @@ int rs_vtrace(int T, int E, float gamma, float lam, float rho_bar, float c_bar, 
 /* PPOModel.train (model.py:179-213), split so that a data-parallel caller can all-reduce between the pieces */
 int rs_adv_moments(const int* idx, int n, const float* returns, const float* values, double* sums, void* stream);
 long long rs_ppo_workspace_floats(int obs_dim, int act_dim, int max_minibatch);
+/* local part of one minibatch (2 launches: tile kernel + deterministic reduction of the per-block partials): grad_stats [P + 4] =
+ * sum over the n local samples of d loss / d theta (divided by global_n) followed by the stat sums (pg, vf, approxkl, clipfrac);
+ * stats5 (may be NULL): stats5[2] receives the policy entropy of the PRE-update parameters */
 int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs, const float* actions, const float* returns,
                 const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
                 const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
-                float* log_ratio, int precision, void* stream);
+                float* log_ratio, double* stats5, int precision, void* stream);
+/* entropy term, global-norm clip (model.py:130-132) and TF-style Adam (model.py:121,139) on the (all-reduced) gradient in ONE
+ * launch; stats5 (may be NULL) receives [pg_loss, vf_loss, ., approxkl, clipfrac] = stat sums / global_n */
 int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
-                 float lr, long long step_t, float beta1, float beta2, float eps, double* scratch, float* gnorm_out, void* stream);
+                 float lr, long long step_t, float beta1, float beta2, float eps, float* gnorm_out, long long global_n, double* stats5,
+                 void* stream);
+/* DATA-PARALLEL minibatch schedule on the device (alg_ppo.py:355-398 over env shards): from the GLOBAL permutation of one epoch
+ * (int32, device; every rank holds the same one) the LOCAL indices of every minibatch that fall in this rank's sample range
+ * [lo, hi): out_idx [nmb][nbatch_train] (minibatch m at out_idx + m * nbatch_train, order preserved), counts [nmb] */
+int rs_epoch_split(const int* perm, long long n_global, int nbatch_train, long long lo, long long hi, int* out_idx, int* counts, void* stream);
+/* advantage moments (model.py:182-185) of ALL minibatches of an epoch in one launch: sums [nmb][2] doubles; idx [nmb][cap] (NULL =
+ * identity over n_total samples), counts [nmb] (NULL = full slices).  Returns and values are constant during an update, so a
+ * data-parallel caller all-reduces these once per epoch instead of once per minibatch */
+int rs_adv_moments_multi(const int* idx, const int* counts, int nmb, int cap, long long n_total, const float* returns, const float* values,
+                         double* sums, void* stream);
 /* the five scalars PPOModel.train returns (model.py:137, loss_names): stats5 = [pg_loss, vf_loss, entropy, approxkl, clipfrac] as
  * doubles, from the (all-reduced) stat sums behind the gradient in grad_stats and the logstd of `params`; call it BEFORE
  * rs_adam_step: the reference evaluates the entropy with the pre-update parameters (same session.run as the train op) */
@@ -153,17 +168,24 @@ int rs_ppo_stats(const float* grad_stats, const float* params, int obs_dim, int 
  * a_lbo,a_sbo,a_step,b_lbo,b_sbo,b_step,nk} (bytes), host pointer */
 int rs_tc_selftest(const int* prm13, const float* A, const float* B, float* D, void* stream);
 
+/* OR of the status bits any env raised since the last clear (out2_host[0]) and the number of env-steps that raised one
+ * (out2_host[1]); HOST pointer, synchronises with `stream`.  Auto-reset clears an env's own status word but not this latch:
+ * check it once per rollout, where mujoco-py's warning callback would have raised inside the worker (builder.py:351-369) */
+int rs_status_latch(rs_env* h, int* out2_host, int clear, void* stream);
+/* env.seed(s) (run.py:73-83, mujoco_env.py:82-84): re-keys the Philox streams of the reset states; env e keeps stream (seed, e) */
+int rs_seed(rs_env* h, unsigned long long seed);
+
 /* diagnostics of the last rs_step: int[E][4] = (Newton iterations, evaluations with an inter-agent contact, contacts) summed over
  * the 20 forward evaluations of the step, and the largest iteration count of a single evaluation (cf. mjData.solver_iter / ncon) */
 int rs_get_diag(rs_env* h, int* diag, void* stream);
 
-/* single-GPU convenience: rs_adv_moments -> rs_ppo_grad -> rs_ppo_stats -> rs_adam_step in ONE call (one host->library transition
- * per minibatch instead of four; a data-parallel caller uses the pieces and all-reduces between them).  beta1 = 0.9, beta2 = 0.999,
- * eps = 1e-5 as model.py:121; adv_sums [2], scratch [1] doubles and grad_stats [P + 8] floats are caller-owned device buffers. */
+/* single-GPU convenience: [rs_adv_moments ->] rs_ppo_grad -> rs_adam_step in ONE call, 3 launches (a data-parallel caller uses the
+ * pieces and all-reduces grad_stats between them).  beta1 = 0.9, beta2 = 0.999, eps = 1e-5 as model.py:121; adv_sums [2] doubles
+ * (already filled when moments_ready != 0, e.g. by rs_adv_moments_multi) and grad_stats [P + 8] floats are caller-owned device buffers. */
 int rs_ppo_minibatch_step(float* params, float* m, float* v, int obs_dim, int act_dim, const float* obs, const float* actions,
                           const float* returns, const float* values, const float* old_nlp, const float* weights, const int* idx, int n,
                           float cliprange, float ent_coef, float vf_coef, float max_grad_norm, float lr, long long step_t,
-                          float* workspace, float* grad_stats, double* adv_sums, double* scratch, float* gnorm_out, double* stats5,
+                          float* workspace, float* grad_stats, double* adv_sums, int moments_ready, float* gnorm_out, double* stats5,
                           float* log_ratio, int precision, void* stream);
 
 /* HOST function (no GPU): the reference's per-epoch minibatch permutation, `np.random.shuffle(inds)` on the legacy global

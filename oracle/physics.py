@@ -14,16 +14,32 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_NATIVE = False
+NATIVE_FLAGS = '-O3 -march=native -funroll-loops'
+PORTABLE_FLAGS = '-O3'
 
 
 def build():
     subprocess.check_call(['make', '-s', '-C', _HERE])
 
 
+def use_native_build():
+    """bench.py's CPU legs: compile the oracle on THIS machine with -O3 -march=native (oracle/Makefile `native`) and load that
+    build instead of the portable one.  Returns the flag string in use.  Must be called before the first lib()."""
+    global _NATIVE
+    assert _LIB is None, "the oracle library is already loaded"
+    try:
+        subprocess.check_call(['make', '-s', '-C', _HERE, 'native'])
+        _NATIVE = True
+        return NATIVE_FLAGS
+    except Exception:
+        return PORTABLE_FLAGS
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, '_build', 'libphysics_oracle.so')
+        path = os.path.join(_HERE, '_build', 'libphysics_oracle_native.so' if _NATIVE else 'libphysics_oracle.so')
         if not os.path.exists(path):
             build()
         L = ctypes.CDLL(path)

@@ -205,3 +205,43 @@ def zoo_mlp_act(flat, obs, D, A):
     rstd = np.sqrt(max(rss / rc - rmean ** 2, 1e-2))
     g = np.tanh(np.tanh(obz @ pi[0] + pi[1]) @ pi[2] + pi[3])
     return g @ pi[4] + pi[5], vz * rstd + rmean
+
+
+def select_training_set(batch, use_opponent_data, vgap, last_version_gap, neglogp_threshold, rho_bar, nbatch):
+    """NumPy restatement of the reference's training-set selection, alg_ppo.py:258-344 (TEST INFRASTRUCTURE).
+
+    `batch`: dict of the Runner outputs as [2, N, ...] arrays (obs, returns, actions, values, neglogpacs) plus the flat
+    off_policy_ratio / ratio [N].  Returns (data dict, weights, usable_index)."""
+    clip_ratio = rho_bar
+    opr = np.array(batch['off_policy_ratio'], dtype=np.float32); tr = np.array(batch['ratio'], dtype=np.float32)
+    opr[np.isnan(opr)] = clip_ratio; opr = np.clip(opr, 0., clip_ratio)                      # alg_ppo.py:262-266
+    tr[np.isnan(tr)] = clip_ratio; tr = np.clip(tr, 0., clip_ratio)                          # alg_ppo.py:276-280
+    usable = np.where(batch['neglogpacs'][1] < neglogp_threshold)[0]                          # alg_ppo.py:286
+    keys = ('obs', 'returns', 'actions', 'values', 'neglogpacs')
+    if use_opponent_data is None or (vgap is not None and last_version_gap > vgap):           # alg_ppo.py:325-330
+        data = {k: batch[k][0] for k in keys}
+    else:
+        data = {k: np.concatenate([batch[k][0], batch[k][1, usable]], axis=0) for k in keys}  # alg_ppo.py:334-335
+    if use_opponent_data is None:
+        weights = np.ones(nbatch, dtype=np.float32)                                           # alg_ppo.py:337-338
+    elif use_opponent_data == 'direct':
+        weights = np.ones(data['obs'].shape[0], dtype=np.float32)
+    elif use_opponent_data == 'off_policy':
+        weights = np.concatenate([np.ones(nbatch, dtype=np.float32), opr[usable]])
+    else:
+        weights = np.concatenate([np.ones(nbatch, dtype=np.float32), tr[usable]])
+    # the epoch loop indexes weights[mbinds] with mbinds < len(data) (alg_ppo.py:378-381), so only this prefix is ever read
+    return data, weights[:data['obs'].shape[0]], usable
+
+
+def ratio_divergence(flat_candidates, flat_current, obs, act, D, A):
+    """alg_ppo.py:228-241: RD_i = mean | action_probability_i / action_probability_current - 1 | where action_probability is the
+    NEGLOGP of the given actions (policies.py:107-108), normalised to sum 1."""
+    m0, _, ls0 = forward(flat_current, obs, D, A)
+    base = neglogp(act, m0, ls0)
+    rd = []
+    for f in flat_candidates:
+        m, _, ls = forward(f, obs, D, A)
+        rd.append(np.abs(neglogp(act, m, ls) / base - 1.).mean())
+    rd = np.array(rd)
+    return rd / rd.sum()

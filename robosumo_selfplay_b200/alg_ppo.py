@@ -19,7 +19,7 @@ import numpy as np
 
 from .model import PPOModel
 from .runner import Runner
-from .dist import split_minibatch, EpochPermutations
+from .dist import EpochPermutations, EpochSchedule
 
 
 def constfn(val):
@@ -151,13 +151,105 @@ def ratio_figure(log_dir, update, idx, raw, nlp, clip_ratio, neglogp_threshold):
     return out
 
 
-def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_opponent_data=None, seed=None, nsteps=2048, ent_coef=0.0,
-          lr=3e-4, vf_coef=0.5, max_grad_norm=0.5, gamma=0.99, lam=0.95, rho_bar=1., c_bar=1., log_interval=10, nminibatches=4,
-          noptepochs=4, cliprange=0.2, save_interval=1, load_path=None, nagent=2, anneal_bound=500, vgap=None, kl_threshold=None,
-          neglogp_threshold=10000., log_dir=None, comm=None, update_fn=None, max_snapshots=30, **network_kwargs):
+class SnapshotRing:
+    """The opponent pool ON THE DEVICE (row N2): every saved version of the learner as one row of an [n_snap, P] float32 tensor in
+    HBM (98 KB each; 2 000 snapshots = 196 MB).  Every rank holds the same rows (parameters are replicated), so choosing an
+    opponent moves an INDEX between ranks, never a parameter vector, and loading it is a device-to-device row copy.  The
+    reference's pool is the checkpoint directory (alg_ppo.py:122-123,217-244,459-464: joblib.load + 13 assign ops per update)."""
+
+    def __init__(self, P, device, capacity=64):
+        import torch
+        self.torch, self.P, self.device = torch, P, device
+        self.buf = torch.empty((capacity, P), dtype=torch.float32, device=device)
+        self.row = {}                                   # version -> row
+
+    def put(self, version, params):
+        if version not in self.row:
+            if len(self.row) == self.buf.shape[0]:
+                nb = self.torch.empty((2 * self.buf.shape[0], self.P), dtype=self.torch.float32, device=self.device)
+                nb[:self.buf.shape[0]].copy_(self.buf)
+                self.buf = nb
+            self.row[version] = len(self.row)
+        self.buf[self.row[version]].copy_(params)
+
+    def get(self, version):
+        return self.buf[self.row[version]]
+
+    def versions(self):
+        return sorted(self.row)
+
+    def __len__(self):
+        return len(self.row)
+
+
+def select_training_set(R, use_opponent_data, vgap, last_version_gap, neglogp_threshold, rho_bar, nbatch_local):
+    """alg_ppo.py:258-344 on device tensors: the IS ratios with NaN -> rho_bar and clipping to [0, rho_bar], the usable opponent
+    samples (neglogp of the opponent's action under the learner below the threshold), and the training set = agent-0 samples
+    followed by the usable agent-1 samples with their importance weights.  Returns (data dict, weights or None, n_usable)."""
     import torch
-    assert network == 'mlp' and nagent == 2
-    assert network_kwargs.get('num_hidden', 64) == 64 and network_kwargs.get('value_network', 'copy') == 'copy'
+    fix = lambda x: torch.clamp(torch.nan_to_num(x, nan=rho_bar), 0.0, rho_bar)
+    keys = ('obs', 'returns', 'actions', 'values', 'neglogpacs')
+    usable = (R['neglogpacs'][1] < neglogp_threshold).nonzero().flatten()
+    if use_opponent_data is None or (vgap is not None and last_version_gap > vgap):
+        return {k: R[k][0].contiguous() for k in keys}, None, int(usable.numel())
+    if use_opponent_data not in ('direct', 'off_policy', 'both'):
+        raise ValueError("use_opponent_data must be None, 'direct', 'off_policy' or 'both'")
+    data = {k: torch.cat([R[k][0], R[k][1][usable]], 0).contiguous() for k in keys}
+    dev = data['returns'].device
+    ones = torch.ones(nbatch_local, dtype=torch.float32, device=dev)
+    if use_opponent_data == 'direct':
+        extra = torch.ones(int(usable.numel()), dtype=torch.float32, device=dev)
+    elif use_opponent_data == 'off_policy':
+        extra = fix(R['off_policy_ratio'])[usable]
+    else:
+        extra = fix(R['ratio'])[usable]
+    return data, torch.cat([ones, extra]).contiguous(), int(usable.numel())
+
+
+def ratio_divergence_weights(policy, ring, versions, base_neglogp, o_obs, o_act):
+    """The sampling weights of opponent_mode='ours' (alg_ppo.py:228-244): mean |p_new / p_base - 1| over the opponent's last batch
+    for every candidate snapshot, where the reference's `action_probability` returns a NEGLOGP (so the ratio is one of
+    neglogps, as in the reference).  The candidate parameters are read in place from the device ring."""
+    keep = policy.params
+    rd = []
+    try:
+        for v in versions:
+            policy.params = ring.get(v)
+            newp = policy.action_probability(o_obs, given_action=o_act)
+            rd.append((newp / base_neglogp - 1.0).abs().double().mean())
+    finally:
+        policy.params = keep
+    import torch
+    return torch.stack(rd)
+
+
+_NETWORK_KWARGS = {'num_hidden': 64, 'value_network': 'copy', 'num_layers': 2}
+
+
+def learn(*, network='mlp', env, total_timesteps, eval_env=None, opponent_mode='ours', use_opponent_data=None, seed=None, nsteps=2048,
+          ent_coef=0.0, lr=3e-4, vf_coef=0.5, max_grad_norm=0.5, gamma=0.99, lam=0.95, rho_bar=1., c_bar=1., log_interval=10,
+          nminibatches=4, noptepochs=4, cliprange=0.2, save_interval=1, load_path=None, nagent=2, anneal_bound=500, vgap=None,
+          kl_threshold=None, neglogp_threshold=10000., fix_opponent_path=None, log_dir=None, comm=None, update_fn=None, max_snapshots=30,
+          strict_status=True, precision='tf32', **network_kwargs):
+    """Signature and defaults of the reference's learn (alg_ppo.py:25-29) with these differences, all deliberate:
+    `nagent` defaults to 2 (the reference's signature says 1 but run.py:181-187 always passes 2, and the loop only works for 2);
+    `model_fn` / `init_fn` / `mpi_rank_weight` are not accepted (one model class; `comm` is this package's dist.Comm);
+    `log_dir`, `update_fn`, `max_snapshots`, `strict_status`, `precision` ('tf32' tensor cores | 'fp32') are additions; `eval_env` is accepted and, as in the reference
+    (alg_ppo.py:346-351 only touches it when set), unused by the default path; network kwargs other than the 2x64 ReLU 'copy'
+    architecture of defaults.py:8-26 raise instead of being ignored."""
+    import torch
+    if network != 'mlp' or nagent != 2:
+        raise ValueError("this path implements network='mlp' with nagent=2 (run.py --algo ppo on RoboSumo)")
+    for k, v in network_kwargs.items():
+        if k == 'activation':
+            if getattr(v, '__name__', str(v)) not in ('relu', 'relu6_not', 'ReLU'):
+                raise ValueError("only activation=relu is implemented (defaults.py:25)")
+        elif k not in _NETWORK_KWARGS:
+            raise TypeError("learn() got an unexpected network keyword %r" % k)
+        elif v != _NETWORK_KWARGS[k]:
+            raise ValueError("%s=%r is not implemented (this path: %s=%r)" % (k, v, k, _NETWORK_KWARGS[k]))
+    if opponent_mode not in ('fix', 'random', 'latest', 'ours'):
+        raise ValueError("opponent_mode must be 'fix', 'random', 'latest' or 'ours'")
     set_global_seeds(seed)
     if isinstance(lr, float): lr = constfn(lr)
     if isinstance(cliprange, float): cliprange = constfn(cliprange)
@@ -174,23 +266,31 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
     nbatch_train = nbatch // nminibatches
     device = getattr(env, 'device', torch.device('cuda', 0))
 
-    mk = lambda scope, trainable: PPOModel(ob_dim=D, ac_dim=A, ent_coef=ent_coef, vf_coef=vf_coef, max_grad_norm=max_grad_norm,
-                                           trainable=trainable, model_scope=scope, device=device, comm=comm if trainable else None)
-    model = mk('model_0', True)                       # creation order = np.random draw order (alg_ppo.py:117-133)
-    models = [model, mk('model_1', False)]
-    model_util = mk('model_util', False)
+    make_model = lambda scope, trainable: PPOModel(ob_dim=D, ac_dim=A, ent_coef=ent_coef, vf_coef=vf_coef, max_grad_norm=max_grad_norm,
+                                                   trainable=trainable, model_scope=scope, device=device, comm=comm if trainable else None,
+                                                   precision=precision)
+    model = make_model('model_0', True)               # creation order = np.random draw order (alg_ppo.py:117-133)
+    models = [model, make_model('model_1', False)]
+    model_util = make_model('model_util', False)
     if comm is not None:
         comm.broadcast(model.params, 0)
     checkdir = osp.join(log_dir, 'checkpoints') if log_dir else None
-    snapshots = {}                                    # version -> flat params (host); the checkpoint directory doubles as the pool
+    ring = SnapshotRing(model.P, device)              # version -> parameters, device resident; the checkpoint files mirror it (rank 0)
     def save(version):
-        snapshots[version] = model.get_flat()
+        ring.put(version, model.params)
         if checkdir and rank == 0:
             model.save(osp.join(checkdir, '%.5i' % version))
     save(0)
     if load_path is not None:
         for m in models:
             m.load(load_path)
+    if opponent_mode == 'fix':
+        # alg_ppo.py:194-206: the opponent is a pretrained policy_zoo MLP for the whole run (the reference passes the MLPPolicy object to
+        # build_policy, which cannot call it -- SURVEY 8f N1; this is the computation that code intends)
+        from .policy_zoo import ZooMLPPolicy, ZooOpponentModel
+        if fix_opponent_path is None:
+            raise ValueError("opponent_mode='fix' needs fix_opponent_path (a policy_zoo agent-params-v*.npy)")
+        models[1] = ZooOpponentModel(ZooMLPPolicy.load(fix_opponent_path, D - 1, A, device), seed=(seed or 0) + 17 * rank)
 
     runner = Runner(env=env, models=models, nsteps=nsteps, nagent=nagent, gamma=gamma, lam=lam, rho_bar=rho_bar, c_bar=c_bar,
                     anneal_bound=anneal_bound, seed=(seed or 0) * 7919 + rank)
@@ -200,9 +300,9 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
     # observability: monitor.csv, fig/ratio_<update>.npz(+png), ratio_summary.pkl -- rank 0 only
     monitor = EpisodeMonitor(log_dir if rank == 0 else None, getattr(env, 'env_id', 'RoboSumo'))
     ratio_log = dict(off_policy_ratio_mean=[], off_policy_ratio_clip_frac=[], off_env_ratio_mean=[], off_env_ratio_clip_frac=[],
-                     total_ratio_mean=[], total_ratio_clip_frac=[], ppo_clip_frac=[], approxkl=[])
-    lo, hi = rank * nbatch_local, (rank + 1) * nbatch_local
+                     total_ratio_mean=[], total_ratio_clip_frac=[], ppo_clip_frac=[], approxkl=[], useful_ratio=[])
     prev = None
+    sched = None
 
     nupdates = total_timesteps // nbatch
     for update in range(1, nupdates + 1):
@@ -211,90 +311,74 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
         frac = 1.0 - (update - 1.0) / nupdates
         lrnow, cliprangenow = lr(frac), cliprange(frac)
 
-        # ---- opponent (alg_ppo.py:192-247); every rank draws from the same np.random stream -> same index ----
-        versions = sorted(snapshots.keys())
-        if update == 1:
+        # ---- opponent (alg_ppo.py:192-247); every rank draws from the same np.random stream ----
+        versions = ring.versions()
+        if update == 1 or opponent_mode == 'fix':
             idx = 0
         elif opponent_mode == 'random':
             idx = int(np.random.choice(update, 1)[0])
         elif opponent_mode == 'latest':
             idx = update - 1
-        elif opponent_mode == 'ours':
-            # ratio-divergence-weighted sampling over <= 30 snapshots (alg_ppo.py:228-244).  The reference call passes the
+        else:
+            # 'ours': ratio-divergence-weighted sampling over <= 30 snapshots (alg_ppo.py:228-244).  The reference call passes the
             # action positionally and the sf01-scrambled opponent_obs, which raises at HEAD; this is the intended computation.
             o_obs, o_act = prev['obs'][1], prev['actions'][1]
             base = models[1].act_model.action_probability(o_obs, given_action=o_act)
             sub = np.sort(np.random.choice(len(versions), max_snapshots, replace=False)) if len(versions) > max_snapshots else np.arange(len(versions))
-            rd = []
-            for i in sub:
-                model_util.set_flat(snapshots[versions[i]])
-                newp = model_util.act_model.action_probability(o_obs, given_action=o_act)
-                rd.append(float((newp / base - 1.0).abs().mean().item()))
-            rd = np.array(rd); rd = rd / rd.sum()
+            rd = ratio_divergence_weights(model_util.act_model, ring, [versions[i] for i in sub], base, o_obs, o_act)
+            if comm is not None:                  # the batch is rank-local: average the divergences so that every rank holds the same weights
+                comm.all_reduce_sum(rd); rd = rd / world
+            rd = rd.cpu().numpy(); rd = rd / rd.sum()
             idx = int(versions[sub[np.random.choice(len(rd), 1, p=rd)[0]]])
-        else:
-            raise NotImplementedError("opponent_mode=%r ('fix' needs the policy_zoo MLP: next row N1)" % opponent_mode)
+            if comm is not None:                  # belt and braces: the index, not a 98 KB vector, is what crosses ranks
+                idx = comm.broadcast_int(idx, 0, device)
         version_gap.append(update - 1 - idx)
-        models[1].set_flat(snapshots[idx])
-        if comm is not None:
-            comm.broadcast(models[1].params, 0)       # opponent-snapshot broadcast over NCCL (98 KB)
+        if opponent_mode != 'fix':
+            models[1].params.copy_(ring.get(idx))        # device-to-device row copy; every rank holds the same ring
 
         # the update's permutations depend on the generator stream only: when the sample count is known up front they are all
         # computed on a helper thread WHILE the rollout runs (nothing else draws from np.random until they are consumed)
-        perms = EpochPermutations(nbatch, noptepochs, ahead=noptepochs) if use_opponent_data is None else None
+        perms = EpochPermutations(nbatch, noptepochs, ahead=noptepochs, dtype=np.int32) if use_opponent_data is None else None
         # ---- rollout (device resident) ----
         R = runner.run(update, as_numpy=False)
         prev = R
+        if hasattr(env, 'check_status'):
+            env.check_status(strict=strict_status)          # NaN / contact-buffer overflow anywhere in the rollout raises here (builder.py:351-369)
         t_roll = time.perf_counter()
         epinfobuf.extend(R['epinfos'])
         monitor.write(R['epinfos'])
         clip_ratio = rho_bar
         raw3 = [torch.nan_to_num(R[k], nan=clip_ratio) for k in ('off_policy_ratio', 'off_env_ratio', 'ratio')]      # alg_ppo.py:258-279
         rstat = torch.stack([torch.stack([x.double().mean(), (x > clip_ratio).double().mean()]) for x in raw3]).cpu().numpy()
-        for (mk, ck), (mean_, frac_) in zip((('off_policy_ratio_mean', 'off_policy_ratio_clip_frac'), ('off_env_ratio_mean', 'off_env_ratio_clip_frac'),
-                                             ('total_ratio_mean', 'total_ratio_clip_frac')), rstat):
-            ratio_log[mk].append(float(mean_)); ratio_log[ck].append(float(frac_))
+        for (mkey, ckey), (mean_, frac_) in zip((('off_policy_ratio_mean', 'off_policy_ratio_clip_frac'), ('off_env_ratio_mean', 'off_env_ratio_clip_frac'),
+                                                 ('total_ratio_mean', 'total_ratio_clip_frac')), rstat):
+            ratio_log[mkey].append(float(mean_)); ratio_log[ckey].append(float(frac_))
         if rank == 0 and log_dir:
             ratio_figure(log_dir, update, idx, raw3, R['neglogpacs'], clip_ratio, neglogp_threshold)
-        fix = lambda x: torch.clamp(torch.nan_to_num(x, nan=clip_ratio), 0.0, clip_ratio)      # alg_ppo.py:258-279
-        off_policy_ratio, total_ratio = fix(R['off_policy_ratio']), fix(R['ratio'])
-        usable = (R['neglogpacs'][1] < neglogp_threshold).nonzero().flatten()
 
         # ---- training set (alg_ppo.py:325-344) ----
-        take0 = lambda k: R[k][0]
-        if use_opponent_data is None or (vgap is not None and version_gap[-1] > vgap):
-            data = {k: take0(k).contiguous() for k in ('obs', 'returns', 'actions', 'values', 'neglogpacs')}
-            weights = None
-        else:
-            assert world == 1, "opponent-data reuse is single-GPU for now"
-            data = {k: torch.cat([R[k][0], R[k][1][usable]], 0).contiguous() for k in ('obs', 'returns', 'actions', 'values', 'neglogpacs')}
-            ones = torch.ones(nbatch, dtype=torch.float32, device=device)
-            extra = {'direct': torch.ones(len(usable), dtype=torch.float32, device=device), 'off_policy': off_policy_ratio[usable],
-                     'both': total_ratio[usable]}[use_opponent_data]
-            weights = torch.cat([ones, extra]).contiguous()
-        n_local = data['returns'].shape[0]
-        update_sample_num = n_local * world if weights is None else n_local
+        data, weights, n_usable = select_training_set(R, use_opponent_data, vgap, version_gap[-1], neglogp_threshold, rho_bar, nbatch_local)
+        ratio_log['useful_ratio'].append(n_usable / float(nbatch_local))
+        n_local = int(data['returns'].shape[0])
+        # data-parallel: rank r owns the contiguous global sample range [lo, hi) (rank-major; with the default agent-0 data this is the
+        # env-major order of one process over all envs).  With opponent data the ranges are ragged: one small all-gather of the sizes.
+        sizes = comm.all_gather_int(n_local, device) if comm is not None else [n_local]
+        lo = int(sum(sizes[:rank])); hi = lo + n_local
+        update_sample_num = int(sum(sizes))
 
         # ---- epochs x minibatches (alg_ppo.py:355-398) ----
         if perms is None:
-            perms = EpochPermutations(update_sample_num, noptepochs)     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
+            perms = EpochPermutations(update_sample_num, noptepochs, dtype=np.int32)     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
         assert perms._inds.shape[0] == update_sample_num
+        if sched is None or sched.n_total != update_sample_num or sched.lo != lo or sched.hi != hi:
+            sched = EpochSchedule(device, update_sample_num, nbatch_train, lo, hi, comm)
         stat_acc = []
         early_stop = False
         for epoch in range(noptepochs):
-            inds = next(perms)
-            starts = list(range(0, update_sample_num, nbatch_train))
-            if world == 1:
-                dev_inds = torch.as_tensor(inds.astype(np.int32), device=device)
-                parts = [(dev_inds[s:s + nbatch_train], min(nbatch_train, update_sample_num - s)) for s in starts]
-            else:
-                loc = [split_minibatch(inds[s:s + nbatch_train], lo, hi) for s in starts]
-                cat = torch.as_tensor(np.concatenate(loc) if len(loc) else np.zeros(0, np.int32), device=device)
-                offs = np.cumsum([0] + [len(x) for x in loc])
-                parts = [(cat[offs[i]:offs[i + 1]], min(nbatch_train, update_sample_num - s)) for i, s in enumerate(starts)]
-            for mb_idx, gn in parts:
+            parts = sched.load(next(perms), data['returns'], data['values'])
+            for mb_idx, n_mb, gn, sums in parts:
                 stats, _ = model.train_indexed(lrnow, cliprangenow, data['obs'], data['returns'], data['actions'], data['values'],
-                                               data['neglogpacs'], weights, mb_idx, global_n=gn)
+                                               data['neglogpacs'], weights, mb_idx, global_n=gn, adv_sums=sums)
                 stat_acc.append(stats)
                 if kl_threshold is not None and float(stats[3].item()) > kl_threshold * 1.5:
                     early_stop = True
@@ -311,7 +395,8 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
                              ratio_log['off_env_ratio_mean'], ratio_log['off_env_ratio_clip_frac'], ratio_log['total_ratio_mean'],
                              ratio_log['total_ratio_clip_frac'][-1] if ratio_log['total_ratio_clip_frac'] else 0.0, ratio_log['ppo_clip_frac'], ratio_log['approxkl']], f)
         tnow = time.perf_counter()
-        history.append(dict(update=update, opponent=idx, rollout_s=t_roll - tstart, update_s=tnow - t_roll, losses=lossvals))
+        history.append(dict(update=update, opponent=idx, rollout_s=t_roll - tstart, update_s=tnow - t_roll, losses=lossvals,
+                            samples=update_sample_num, usable=n_usable))
         if update_fn is not None:
             update_fn(update)
         if update % log_interval == 0 or update == 1:
@@ -335,4 +420,5 @@ def learn(*, network='mlp', env, total_timesteps, opponent_mode='random', use_op
     monitor.close()
     model.history = history
     model.ratio_log = ratio_log
+    model.snapshots = ring
     return model

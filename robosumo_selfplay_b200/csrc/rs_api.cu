@@ -59,6 +59,7 @@ struct EnvDev {
     int E;
     float *qpos, *qvel, *warm, *ep_ret, *ep_dret;
     int* pred;                         // active-set prediction carried across steps: [E][4 + MAXC/2] = limit masks (non-zero, negative side, loaded), nprev, cprev pairs
+    int* latch;                        // [2]: OR of every status bit any env raised since the last rs_status_latch(clear) -- auto-reset does not clear it; number of env-steps that raised one
     int *ep_step, *status, *diag;      // diag[E][4]: Newton iterations, coupled evaluations, contacts summed over the last env step, max iterations of one evaluation
     unsigned int* ep_count;
     const rs_agent_model* am;
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     const int OD = (7 + 2*LA) + (6 + 2*LA) + 6 * (1 + 3*LA) + 14 + (7 + 2*LB) + (6 + 2*LB) + 6 * (1 + 3*LB) + 14;
     RS_SYNC();
     int st = s.status;
+    if (lane == 0) { const int fresh = st & ~d.status[e] & 7; if (fresh) { atomicOr(d.latch, fresh); atomicAdd(d.latch + 1, 1); } }      // bits raised during THIS step
     if (o.done[0] && auto_reset) {
         unsigned int ep = d.ep_count[e] + 1;
         env_reset_state(c, d.P, (uint32_t)e, ep);
@@ -322,6 +324,9 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     h->wpb = (int)((227 * 1024 - 2 * sizeof(rs_agent_model)) / sb);
     if (h->wpb > RS_WPB) h->wpb = RS_WPB;
     if (h->wpb < 1) { delete h; return fail(RS_ERR_UNSUPPORTED, "slab does not fit in shared memory%s", ""); }
+    // the dynamic shared-memory limit is an attribute of the KERNEL (template instance), not of this handle: opt in to what the
+    // largest block of this morphology needs, so that a small env created later cannot lower the limit under a large one
+    const size_t smem_max = sb * h->wpb;
     {   // fewer pairs than one wave can hold: spread them over all SMs (fewer warps per block = less issue contention) instead
         // of filling some SMs and leaving others idle.  (With two or more waves an even split measured slower: the block
         // scheduler backfills finished SMs anyway.)
@@ -346,16 +351,17 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     CUDA_OK(cudaMalloc(&d.ep_dret, sizeof(float) * E)); CUDA_OK(cudaMalloc(&d.ep_step, sizeof(int) * E));
     CUDA_OK(cudaMalloc(&d.status, sizeof(int) * E)); CUDA_OK(cudaMalloc(&d.ep_count, sizeof(unsigned int) * E));
     CUDA_OK(cudaMalloc(&d.diag, sizeof(int) * E * 4)); CUDA_OK(cudaMemset(d.diag, 0, sizeof(int) * E * 4));
+    CUDA_OK(cudaMalloc(&d.latch, sizeof(int) * 2)); CUDA_OK(cudaMemset(d.latch, 0, sizeof(int) * 2));
     CUDA_OK(cudaMemset(d.qpos, 0, sizeof(float) * E * h->nq)); CUDA_OK(cudaMemset(d.qvel, 0, sizeof(float) * E * h->nv));
     CUDA_OK(cudaMemset(d.warm, 0, sizeof(float) * E * h->nv)); CUDA_OK(cudaMemset(d.ep_ret, 0, sizeof(float) * E));
     CUDA_OK(cudaMemset(d.ep_dret, 0, sizeof(float) * E)); CUDA_OK(cudaMemset(d.ep_step, 0, sizeof(int) * E));
     CUDA_OK(cudaMemset(d.status, 0, sizeof(int) * E)); CUDA_OK(cudaMemset(d.ep_count, 0, sizeof(unsigned int) * E));
     int rc = dispatch(h, [&](auto la, auto lb) {
         constexpr int A = decltype(la)::value, B = decltype(lb)::value;
-        CUDA_OK(cudaFuncSetAttribute(k_step<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        CUDA_OK(cudaFuncSetAttribute(k_reset<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        CUDA_OK(cudaFuncSetAttribute(k_set_state<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        CUDA_OK(cudaFuncSetAttribute(k_forward_debug<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CUDA_OK(cudaFuncSetAttribute(k_step<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CUDA_OK(cudaFuncSetAttribute(k_reset<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CUDA_OK(cudaFuncSetAttribute(k_set_state<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CUDA_OK(cudaFuncSetAttribute(k_forward_debug<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         return RS_OK;
     });
     if (rc) { delete h; return rc; }
@@ -375,7 +381,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
 void rs_destroy(rs_env* h) {
     if (!h) return;
     cudaFree(h->d_am); cudaFree(h->d.qpos); cudaFree(h->d.qvel); cudaFree(h->d.warm); cudaFree(h->d.pred); cudaFree(h->d.ep_ret);
-    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.diag); cudaFree(h->d.status); cudaFree(h->d.ep_count);
+    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.diag); cudaFree(h->d.latch); cudaFree(h->d.status); cudaFree(h->d.ep_count);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_epi); cudaFreeHost(h->h_done);
     cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_epi); cudaFree(h->s_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -471,6 +477,26 @@ int rs_step_host(rs_env* h, const float* actions, float* obs, float* rew, uint8_
 int rs_get_diag(rs_env* h, int* diag, void* stream) {
     if (!h || !diag) return fail(RS_ERR_ARG, "rs_get_diag: bad argument%s", "");
     CUDA_OK(cudaMemcpyAsync(diag, h->d.diag, sizeof(int) * h->d.E * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return RS_OK;
+}
+
+/* OR of the status bits raised by any env since the last clear (out[0]) and how many env-steps raised one (out[1]); HOST
+ * pointer, synchronises with `stream`.  Auto-reset wipes the per-env status word, not this latch: the caller checks it once per
+ * rollout, where mujoco-py's warning callback would have raised MujocoException inside the worker (builder.py:351-369). */
+int rs_status_latch(rs_env* h, int* out2_host, int clear, void* stream) {
+    if (!h || !out2_host) return fail(RS_ERR_ARG, "rs_status_latch: bad argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(out2_host, h->d.latch, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    if (clear) CUDA_OK(cudaMemsetAsync(h->d.latch, 0, sizeof(int) * 2, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return RS_OK;
+}
+/* env.seed(s) of the reference (run.py:73-83: env i is seeded seed + i; mujoco_env.py:82-84): re-keys the Philox streams that
+ * draw the reset states; env e keeps its own stream (seed, e).  Takes effect at the next reset / auto-reset. */
+int rs_seed(rs_env* h, unsigned long long seed) {
+    if (!h) return fail(RS_ERR_ARG, "rs_seed: null handle%s", "");
+    h->cfg.seed = seed;
+    h->d.P.seed_lo = (uint32_t)seed; h->d.P.seed_hi = (uint32_t)(seed >> 32);
     return RS_OK;
 }
 
@@ -630,11 +656,16 @@ long long rs_ppo_workspace_floats(int obs_dim, int act_dim, int max_minibatch) {
 int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs, const float* actions, const float* returns,
                 const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
                 const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
-                float* log_ratio, int precision, void* stream) {
+                float* log_ratio, double* stats5, int precision, void* stream) {
     if (!params || !obs || !grad_stats || !workspace || act_dim > RSL_HW || n < 0 || global_n <= 0) return fail(RS_ERR_ARG, "rs_ppo_grad: bad argument%s", "");
     const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { CUDA_OK(cudaMemsetAsync(grad_stats, 0, sizeof(float) * (L.P + 4), st)); return RS_OK; }
+    if (n == 0) {      // this rank holds no sample of the minibatch: zero contribution (the entropy still comes from the parameters)
+        rsl::k_grad_reduce2<<<(L.P + 255) / 256, 256, 0, st>>>(workspace, workspace, 0, L.P, grad_stats, params, L.logstd, act_dim, stats5);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return RS_OK;
+    }
     if (precision == 1 && rsl::tc_tile_bytes(obs_dim) > 227 * 1024) precision = 0;     // wide observations: FP32-pipe kernel
     size_t sm = precision == 1 ? rsl::tc_tile_bytes(obs_dim) : rsl::tile_bytes(obs_dim, act_dim);
     if (sm > 227 * 1024) return fail(RS_ERR_UNSUPPORTED, "rs_ppo_grad: obs_dim too large for one tile%s", "");
@@ -652,22 +683,24 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
     a.gpart = workspace; a.spart = workspace + (size_t)nb * L.P; a.log_ratio = log_ratio;
     if (precision == 1) rsl::k_ppo_tile_tc<<<nb, RSL_TC_THREADS, sm, st>>>(a);
     else rsl::k_ppo_tile<<<nb, RSL_TILE, sm, st>>>(a);
-    rsl::k_grad_reduce<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, grad_stats + L.P);
+    rsl::k_grad_reduce2<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, params, L.logstd, act_dim, stats5);
     g_launches += 2;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
 }
 
-/* entropy term, global-norm clip and TF-style Adam on the (all-reduced) gradient.  step_t counts from 1.  scratch: 2 doubles. */
+/* entropy term, global-norm clip and TF-style Adam on the (all-reduced) gradient, ONE launch; also finalises the statistics
+ * [pg_loss, vf_loss, ., approxkl, clipfrac] from the stat sums behind the gradient when stats5 != NULL.  step_t counts from 1. */
 int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
-                 float lr, long long step_t, float beta1, float beta2, float eps, double* scratch, float* gnorm_out, void* stream) {
-    if (!params || !m || !v || !grad || !scratch || step_t < 1) return fail(RS_ERR_ARG, "rs_adam_step: bad argument%s", "");
+                 float lr, long long step_t, float beta1, float beta2, float eps, float* gnorm_out, long long global_n, double* stats5,
+                 void* stream) {
+    if (!params || !m || !v || !grad || step_t < 1 || (stats5 && global_n < 1)) return fail(RS_ERR_ARG, "rs_adam_step: bad argument%s", "");
     const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
     cudaStream_t st = (cudaStream_t)stream;
-    rsl::k_grad_finish<<<1, 1024, 0, st>>>(grad, L.P, ent_coef, act_dim, L.logstd, scratch);
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step_t)) / (1.0 - pow((double)beta1, (double)step_t));
-    rsl::k_adam<<<(L.P + 255) / 256, 256, 0, st>>>(params, m, v, grad, scratch, L.P, max_grad_norm, (float)lr_t, beta1, beta2, eps, gnorm_out);
-    g_launches += 2;
+    rsl::k_adam2<<<(L.P + 255) / 256, 256, 0, st>>>(params, m, v, grad, L.P, ent_coef, act_dim, L.logstd, max_grad_norm, (float)lr_t, beta1, beta2, eps,
+                                                    gnorm_out, stats5 ? 1.0 / (double)global_n : 0.0, stats5);
+    g_launches += 1;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
 }
@@ -684,15 +717,33 @@ int rs_ppo_stats(const float* grad_stats, const float* params, int obs_dim, int 
 int rs_ppo_minibatch_step(float* params, float* m, float* v, int obs_dim, int act_dim, const float* obs, const float* actions,
                           const float* returns, const float* values, const float* old_nlp, const float* weights, const int* idx, int n,
                           float cliprange, float ent_coef, float vf_coef, float max_grad_norm, float lr, long long step_t,
-                          float* workspace, float* grad_stats, double* adv_sums, double* scratch, float* gnorm_out, double* stats5,
+                          float* workspace, float* grad_stats, double* adv_sums, int moments_ready, float* gnorm_out, double* stats5,
                           float* log_ratio, int precision, void* stream) {
-    int rc = rs_adv_moments(idx, n, returns, values, adv_sums, stream);
-    if (rc) return rc;
+    int rc = RS_OK;
+    if (!moments_ready) { rc = rs_adv_moments(idx, n, returns, values, adv_sums, stream); if (rc) return rc; }
     rc = rs_ppo_grad(params, obs_dim, act_dim, obs, actions, returns, values, old_nlp, weights, idx, n, n, adv_sums, cliprange, ent_coef,
-                     vf_coef, workspace, grad_stats, log_ratio, precision, stream);
+                     vf_coef, workspace, grad_stats, log_ratio, stats5, precision, stream);
     if (rc) return rc;
-    if (stats5) { rc = rs_ppo_stats(grad_stats, params, obs_dim, act_dim, n, stats5, stream); if (rc) return rc; }
-    return rs_adam_step(params, m, v, grad_stats, obs_dim, act_dim, ent_coef, max_grad_norm, lr, step_t, 0.9f, 0.999f, 1e-5f, scratch, gnorm_out, stream);
+    return rs_adam_step(params, m, v, grad_stats, obs_dim, act_dim, ent_coef, max_grad_norm, lr, step_t, 0.9f, 0.999f, 1e-5f, gnorm_out, n, stats5, stream);
+}
+
+/* data-parallel minibatch schedule: local index lists of every minibatch of an epoch from the global permutation (device) */
+int rs_epoch_split(const int* perm, long long n_global, int nbatch_train, long long lo, long long hi, int* out_idx, int* counts, void* stream) {
+    if (!perm || !out_idx || !counts || n_global <= 0 || nbatch_train <= 0 || hi < lo) return fail(RS_ERR_ARG, "rs_epoch_split: bad argument%s", "");
+    const int nmb = (int)((n_global + nbatch_train - 1) / nbatch_train);
+    rsl::k_epoch_split<<<nmb, 1024, 0, (cudaStream_t)stream>>>(perm, n_global, nbatch_train, lo, hi, out_idx, counts);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+/* advantage moments of all minibatches of an epoch: sums[nmb][2]; idx [nmb][cap] or NULL (identity), counts [nmb] or NULL (full slices of n_total) */
+int rs_adv_moments_multi(const int* idx, const int* counts, int nmb, int cap, long long n_total, const float* returns, const float* values,
+                         double* sums, void* stream) {
+    if (nmb <= 0 || cap <= 0 || !returns || !values || !sums) return fail(RS_ERR_ARG, "rs_adv_moments_multi: bad argument%s", "");
+    rsl::k_adv_moments_multi<<<nmb, 1024, 0, (cudaStream_t)stream>>>(idx, counts, cap, n_total, returns, values, sums);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
 }
 
 // ---- legacy NumPy shuffle replay (host) -----------------------------------------------------------------------------------

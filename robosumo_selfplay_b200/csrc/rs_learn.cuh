@@ -232,7 +232,8 @@ __global__ void k_vtrace(int T, int E, float gamma, float lam, float rho_bar, fl
             float offe = expf(nlp[o] - opp_nlp[o]);                  // exp(nlp[0] - opp_nlp[0])    runner.py:171
             float ratio = offp * offe;
             if (ratios && agt == 0) { ratios[o] = offp; ratios[TE + o] = offe; ratios[2 * TE + o] = ratio; }
-            if (agt == 1) { rho = fminf(ratio, rho_bar); cc = fminf(ratio, c_bar); }
+            // np.clip / np.minimum propagate a NaN ratio (runner.py:176-181); fminf would silently return the bound
+            if (agt == 1) { rho = ratio != ratio ? ratio : fminf(ratio, rho_bar); cc = ratio != ratio ? ratio : fminf(ratio, c_bar); }
         }
         cc *= lam;
         const float v = values[(size_t)agt * TE + o], r = rewards[(size_t)agt * TE + o];
@@ -461,54 +462,6 @@ __global__ void __launch_bounds__(RSL_TILE) k_ppo_tile(PPOArgs a) {
     if (threadIdx.x < 4) a.spart[(size_t)blockIdx.x * 8 + threadIdx.x] = t.dout[threadIdx.x * 4] + t.dout[threadIdx.x * 4 + 1] + t.dout[threadIdx.x * 4 + 2] + t.dout[threadIdx.x * 4 + 3];
 }
 
-// reduce the per-block partials in block order (deterministic): grad[P] and stats[4] (sums over the local samples)
-__global__ void k_grad_reduce(const float* __restrict__ gpart, const float* __restrict__ spart, int nblocks, int P,
-                              float* __restrict__ grad, float* __restrict__ stats) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) {
-        float s = 0.f;
-        for (int b = 0; b < nblocks; b++) s += gpart[(size_t)b * P + i];
-        grad[i] = s;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 4) {
-        float s = 0.f;
-        for (int b = 0; b < nblocks; b++) s += spart[(size_t)b * 8 + threadIdx.x];
-        stats[threadIdx.x] = s;
-    }
-}
-// sum of squares of the (all-reduced) gradient, with the entropy term folded in: gsq[0] (double, single block -> deterministic)
-__global__ void k_grad_finish(float* __restrict__ grad, int P, float ent_coef, int A, int logstd_off, double* __restrict__ gsq) {
-    double sq = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        float g = grad[i];
-        if (i >= logstd_off && i < logstd_off + A) { g -= ent_coef; grad[i] = g; }     // - ent_coef * d entropy / d logstd
-        sq += (double)g * (double)g;
-    }
-    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    __shared__ double sh[32];
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
-    __syncthreads();
-    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (blockDim.x >> 5); w++) t += sh[w]; *gsq = t; }
-}
-
-// clip_by_global_norm (model.py:130-132) + tf.train.AdamOptimizer(lr, epsilon=1e-5) (model.py:121,139):
-// lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  theta -= lr_t * m / (sqrt(v) + eps)
-__global__ void k_adam(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ grad,
-                       const double* __restrict__ gsq, int P, float max_grad_norm, float lr_t, float b1, float b2, float eps,
-                       float* __restrict__ gnorm_out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float gn = (float)sqrt(*gsq);
-    float scale = 1.f;
-    if (max_grad_norm > 0.f) scale = max_grad_norm / fmaxf(gn, max_grad_norm);
-    if (i == 0 && gnorm_out) *gnorm_out = gn;
-    if (i >= P) return;
-    const float g = grad[i] * scale;
-    const float mi = b1 * m[i] + (1.f - b1) * g;
-    const float vi = b2 * v[i] + (1.f - b2) * g * g;
-    m[i] = mi; v[i] = vi;
-    params[i] -= lr_t * mi / (sqrtf(vi) + eps);
-}
-
 // trajectory writes of one rollout step (runner.py:70-72,95-100): before the env step the observation and done flags the policies
 // acted on, after it the reward terms and the episode records
 __global__ void k_traj_pre(int E, int D, int t, int T, const float* __restrict__ obs, const uint8_t* __restrict__ done,
@@ -542,6 +495,124 @@ __global__ void k_ppo_stats(const float* __restrict__ grad_stats, const float* _
         out[0] = (double)grad_stats[P] * inv_n; out[1] = (double)grad_stats[P + 1] * inv_n; out[2] = ent;
         out[3] = (double)grad_stats[P + 2] * inv_n; out[4] = (double)grad_stats[P + 3] * inv_n;
     }
+}
+
+// ---- data-parallel minibatch schedule on the device ---------------------------------------------------------------------------
+// Every rank holds the same GLOBAL permutation of an epoch (the reference's np.random.shuffle, replayed bit-exactly on the host
+// and uploaded once per epoch).  Minibatch m is the slice perm[m * nbt, (m + 1) * nbt); this kernel keeps, in order, the entries
+// that fall in this rank's sample range [lo, hi) as LOCAL indices: out_idx[m][0 .. counts[m]).  One block per minibatch, stable
+// compaction by ballot / prefix sums (replaces the NumPy boolean masks over the global index array of round 1).
+__global__ void __launch_bounds__(1024) k_epoch_split(const int* __restrict__ perm, long long N, int nbt, long long lo, long long hi,
+                                                      int* __restrict__ out_idx, int* __restrict__ counts) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int m = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long s0 = (long long)m * nbt, s1 = s0 + nbt < N ? s0 + nbt : N;
+    int* out = out_idx + (long long)m * nbt;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (long long p0 = s0; p0 < s1; p0 += blockDim.x) {
+        const long long p = p0 + threadIdx.x;
+        long long v = -1;
+        if (p < s1) v = perm[p];
+        const bool in = v >= lo && v < hi;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int rank = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int off = 0;
+        for (int q = 0; q < w; q++) off += wsum[q];
+        const int base = base_s;
+        if (in) out[base + off + rank] = (int)(v - lo);
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += wsum[q]; base_s = base + t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[m] = base_s;
+}
+// advantage moments of ALL minibatches of an epoch in one launch (returns and values do not change during the update, so the
+// per-minibatch normalisation of model.py:182-185 needs no launch -- and, data-parallel, no collective -- per minibatch):
+// sums[m] = (sum adv, sum adv^2) over idx[m * cap + 0 .. n_m), n_m = counts[m] or, without counts, the slice length.
+// One block per minibatch, fixed reduction order (deterministic).
+__global__ void __launch_bounds__(1024) k_adv_moments_multi(const int* __restrict__ idx, const int* __restrict__ counts, int cap, long long n_total,
+                                                            const float* __restrict__ returns, const float* __restrict__ values, double* __restrict__ sums) {
+    const int m = blockIdx.x;
+    long long n = counts ? counts[m] : (n_total - (long long)m * cap < cap ? n_total - (long long)m * cap : cap);
+    const int* ix = idx ? idx + (long long)m * cap : nullptr;
+    double s = 0, s2 = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long g = ix ? ix[i] : (long long)m * cap + i;
+        const double a = (double)returns[g] - (double)values[g];
+        s += a; s2 += a * a;
+    }
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    __shared__ double sh[2][32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = s; sh[1][w] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0, t2 = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) { t += sh[0][q]; t2 += sh[1][q]; }
+        sums[2 * m] = t; sums[2 * m + 1] = t2;
+    }
+}
+
+// ---- fused minibatch epilogue: two launches instead of four --------------------------------------------------------------------
+// (1) per-block partials -> grad_stats [P + 4] in block order (deterministic) and, by block 0, the entropy of the PRE-update
+//     parameters into stats5[2] (model.py:137 evaluates it in the same session.run as the train op);
+// (2) after the data-parallel all-reduce (if any): entropy term, global norm, clip, TF-style Adam and the other four statistics.
+//     Every block recomputes the sum of squares over the whole gradient in the same fixed order (24.5 k numbers: cheaper than a
+//     separate single-block launch plus its launch gap, and deterministic).
+__global__ void k_grad_reduce2(const float* __restrict__ gpart, const float* __restrict__ spart, int nblocks, int P,
+                               float* __restrict__ grad, const float* __restrict__ params, int logstd_off, int A, double* __restrict__ stats5) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) {
+        float s = 0.f;
+        for (int b = 0; b < nblocks; b++) s += gpart[(size_t)b * P + i];
+        grad[i] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        float s = 0.f;
+        for (int b = 0; b < nblocks; b++) s += spart[(size_t)b * 8 + threadIdx.x];
+        grad[P + threadIdx.x] = s;
+    }
+    if (stats5 && blockIdx.x == 0 && threadIdx.x == 32) {
+        double ent = 0;
+        for (int q = 0; q < A; q++) ent += (double)params[logstd_off + q] + 1.4189385332046727;      // 0.5 * log(2 pi e)
+        stats5[2] = ent;
+    }
+}
+__global__ void __launch_bounds__(256) k_adam2(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, float* __restrict__ grad,
+                                               int P, float ent_coef, int A, int logstd_off, float max_grad_norm, float lr_t, float b1, float b2,
+                                               float eps, float* __restrict__ gnorm_out, double inv_n, double* __restrict__ stats5) {
+    __shared__ double sh[8];
+    double sq = 0;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+        float g = grad[j];
+        if (j >= logstd_off && j < logstd_off + A) g -= ent_coef;                      // - ent_coef * d entropy / d logstd
+        sq += (double)g * (double)g;
+    }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    double tot = 0;
+    for (int q = 0; q < 8; q++) tot += sh[q];
+    const float gn = (float)sqrt(tot);
+    float scale = 1.f;
+    if (max_grad_norm > 0.f) scale = max_grad_norm / fmaxf(gn, max_grad_norm);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (gnorm_out) *gnorm_out = gn;
+        if (stats5) { stats5[0] = (double)grad[P] * inv_n; stats5[1] = (double)grad[P + 1] * inv_n; stats5[3] = (double)grad[P + 2] * inv_n; stats5[4] = (double)grad[P + 3] * inv_n; }
+    }
+    if (i >= P) return;
+    float g0 = grad[i];
+    if (i >= logstd_off && i < logstd_off + A) { g0 -= ent_coef; }
+    const float g = g0 * scale;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    params[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
 }  // namespace rsl

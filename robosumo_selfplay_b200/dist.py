@@ -38,6 +38,27 @@ class Comm:
         if self.world > 1:
             self.dist.barrier()
 
+    def all_gather_int(self, value, device=None):
+        """[value of rank 0, ..., value of rank world-1] as a list of Python ints (one small collective)."""
+        if self.world == 1:
+            return [int(value)]
+        t = self.torch
+        dev = device if device is not None else (t.device('cuda', self.local_rank) if t.cuda.is_available() and self.dist.get_backend() == 'nccl' else 'cpu')
+        x = t.zeros(self.world, dtype=t.int64, device=dev)
+        x[self.rank] = int(value)
+        self.dist.all_reduce(x, op=self.dist.ReduceOp.SUM)
+        return [int(v) for v in x.cpu().tolist()]
+
+    def broadcast_int(self, value, src=0, device=None):
+        """rank `src`'s Python int on every rank."""
+        if self.world == 1:
+            return int(value)
+        t = self.torch
+        dev = device if device is not None else (t.device('cuda', self.local_rank) if t.cuda.is_available() and self.dist.get_backend() == 'nccl' else 'cpu')
+        x = t.tensor([int(value)], dtype=t.int64, device=dev)
+        self.dist.broadcast(x, src=src)
+        return int(x.item())
+
     def shard(self, n_global):
         """Contiguous env range of this rank: [lo, hi)."""
         per = n_global // self.world
@@ -51,6 +72,61 @@ def split_minibatch(global_idx, lo, hi):
     g = np.asarray(global_idx)
     m = (g >= lo) & (g < hi)
     return (g[m] - lo).astype(np.int32)
+
+
+class EpochSchedule:
+    """The minibatch schedule of one epoch ON THE DEVICE (replaces the per-minibatch NumPy masks of round 1).
+
+    Every rank uploads the same global permutation once per epoch (int32, through a page-locked staging buffer); on one GPU a
+    minibatch is a slice of it, on several `rs_epoch_split` compacts, per minibatch and in order, the entries of this rank's sample
+    range [lo, hi) into local indices.  `rs_adv_moments_multi` then computes the advantage moments of ALL minibatches in one
+    launch and, data-parallel, they are all-reduced ONCE per epoch (returns and values are constant during an update), so a
+    minibatch step costs exactly one collective: the flat gradient.  `parts()` hands out (idx, n_local, n_global, adv_sums)."""
+
+    def __init__(self, device, n_total, nbatch_train, lo=0, hi=None, comm=None):
+        import torch
+        from . import _lib
+        self.t, self.L, self._lib = torch, _lib.lib(), _lib
+        self.device, self.comm = device, comm
+        self.n_total, self.nbt = int(n_total), int(nbatch_train)
+        self.lo, self.hi = int(lo), int(n_total if hi is None else hi)
+        self.world = comm.world if comm is not None else 1
+        self.nmb = (self.n_total + self.nbt - 1) // self.nbt
+        self.perm = torch.empty(self.n_total, dtype=torch.int32, device=device)
+        self.stage = torch.empty(self.n_total, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        self.sums = torch.empty((self.nmb, 2), dtype=torch.float64, device=device)
+        self.copied = None
+        if self.world > 1:
+            self.idx = torch.empty(self.nmb * self.nbt, dtype=torch.int32, device=device)
+            self.counts = torch.empty(self.nmb, dtype=torch.int32, device=device)
+
+    def _p(self, x):
+        import ctypes
+        return ctypes.c_void_p(x.data_ptr()) if x is not None else None
+
+    def load(self, perm, returns, values):
+        """perm: the epoch's global permutation (numpy, any integer dtype).  Returns the list of minibatch parts."""
+        import ctypes
+        import numpy as np
+        t = self.t
+        if self.copied is not None:
+            self.copied.synchronize()                       # the previous upload has left the staging buffer
+        np.copyto(self.stage.numpy(), perm, casting='unsafe')
+        self.perm.copy_(self.stage, non_blocking=True)
+        if t.cuda.is_available():
+            self.copied = t.cuda.Event(); self.copied.record(t.cuda.current_stream(self.device))
+        st = ctypes.c_void_p(t.cuda.current_stream(self.device).cuda_stream)
+        sizes = [min(self.nbt, self.n_total - m * self.nbt) for m in range(self.nmb)]
+        if self.world == 1:
+            self._lib.check(self.L.rs_adv_moments_multi(self._p(self.perm), None, self.nmb, self.nbt, self.n_total, self._p(returns), self._p(values),
+                                                        self._p(self.sums), st))
+            return [(self.perm[m * self.nbt:m * self.nbt + sizes[m]], sizes[m], sizes[m], self.sums[m]) for m in range(self.nmb)]
+        self._lib.check(self.L.rs_epoch_split(self._p(self.perm), self.n_total, self.nbt, self.lo, self.hi, self._p(self.idx), self._p(self.counts), st))
+        self._lib.check(self.L.rs_adv_moments_multi(self._p(self.idx), self._p(self.counts), self.nmb, self.nbt, self.n_total, self._p(returns),
+                                                    self._p(values), self._p(self.sums), st))
+        self.comm.all_reduce_sum(self.sums)                 # ONE collective per epoch for all advantage moments
+        counts = self.counts.cpu().tolist()                 # one small D2H per epoch: the launch geometry of the local parts
+        return [(self.idx[m * self.nbt:m * self.nbt + counts[m]], counts[m], sizes[m], self.sums[m]) for m in range(self.nmb)]
 
 
 def legacy_shuffle(inds):
@@ -80,8 +156,9 @@ class EpochPermutations:
     so an early stop (kl_threshold) leaves the stream exactly where the reference would: nothing speculative is committed.
     Nobody else may draw from `np.random` between construction and the last `next()` (the rollout and the update do not)."""
 
-    def __init__(self, n, nepochs, ahead=1):
+    def __init__(self, n, nepochs, ahead=1, dtype=None):
         import numpy as np
+        self._dtype = dtype                 # e.g. np.int32: the helper thread hands out the permutation already narrowed for the device upload
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
         name, key, pos, self._hg, self._cg = np.random.get_state()
@@ -102,7 +179,7 @@ class EpochPermutations:
         _lib.check(_lib.lib().rs_legacy_shuffle(ctypes.c_void_p(self._key.ctypes.data), ctypes.byref(p),
                                                 ctypes.c_void_p(self._inds.ctypes.data), ctypes.c_longlong(self._inds.shape[0])))
         self._pos = p.value
-        return self._inds.copy(), self._key.copy(), self._pos
+        return (self._inds.copy() if self._dtype is None else self._inds.astype(self._dtype)), self._key.copy(), self._pos
 
     def _launch(self):
         if self._left > 0:

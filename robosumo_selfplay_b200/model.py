@@ -8,6 +8,7 @@ Checkpoints are the reference's: `joblib.dump(list_of_13_float32_arrays)` in tf.
 import ctypes
 import os
 import types
+import zlib
 
 import numpy as np
 
@@ -26,6 +27,8 @@ class PPOModel:
         self.P = param_count(ob_dim, ac_dim)
         self.scope = model_scope
         self.device = torch.device('cuda', device) if not isinstance(device, torch.device) else device
+        if self.device.index is not None:
+            torch.cuda.set_device(self.device)      # one process per GPU: the library's launches go to the calling thread's current device
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), max_grad_norm
         self.trainable = trainable
         self.comm = comm                        # robosumo_selfplay_b200.dist.Comm or None
@@ -33,7 +36,7 @@ class PPOModel:
         assert self._L.rs_param_count(ob_dim, ac_dim) == self.P
         self.params = torch.as_tensor(init_params(ob_dim, ac_dim), device=self.device)       # consumes np.random like ortho_init
         self.precision = precision
-        self.act_model = PolicyWithValue(self.params, ob_dim, ac_dim, seed=abs(hash(model_scope)) % 9973, precision=precision)
+        self.act_model = PolicyWithValue(self.params, ob_dim, ac_dim, seed=zlib.crc32(model_scope.encode()) % 9973, precision=precision)
         self.train_model = types.SimpleNamespace(X=types.SimpleNamespace(dtype=types.SimpleNamespace(name='float32')))
         self.step = self.act_model.step
         self.value = self.act_model.value
@@ -42,9 +45,8 @@ class PPOModel:
             self.m = torch.zeros(self.P, dtype=torch.float32, device=self.device)
             self.v = torch.zeros(self.P, dtype=torch.float32, device=self.device)
             self.t = 0
-            self.grad_stats = torch.zeros(self.P + 4, dtype=torch.float32, device=self.device)
+            self.grad_stats = torch.zeros(self.P + 8, dtype=torch.float32, device=self.device)
             self.adv_sums = torch.zeros(2, dtype=torch.float64, device=self.device)
-            self.scratch = torch.zeros(2, dtype=torch.float64, device=self.device)
             self.gnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
             self._ws = None
             self._ws_mb = 0
@@ -71,42 +73,44 @@ class PPOModel:
         return t.as_tensor(np.ascontiguousarray(x), device=self.device).to(dtype).contiguous()
 
     # ---- training ---------------------------------------------------------------------------
-    def train_indexed(self, lr, cliprange, obs, returns, actions, values, neglogpacs, weights, idx, global_n=None, want_log_ratio=False):
+    def train_indexed(self, lr, cliprange, obs, returns, actions, values, neglogpacs, weights, idx, global_n=None, want_log_ratio=False,
+                      adv_sums=None):
         """One minibatch step on device-resident flat sample arrays; the minibatch is `idx` (int32 device tensor of LOCAL
-        sample indices).  With a communicator, every rank passes its local part of the global minibatch and `global_n`."""
+        sample indices).  With a communicator, every rank passes its local part of the global minibatch and `global_n`.
+        `adv_sums` (device double[2]): the minibatch's GLOBAL advantage moments when the caller already has them
+        (dist.EpochSchedule computes those of a whole epoch in one launch and all-reduces them once); otherwise they are computed
+        (and all-reduced) here.  Launches per step: 2 (gradient tiles + reduction) + [NCCL all-reduce] + 1 (clip + Adam + stats)."""
         t = self.torch
         n = int(idx.numel()) if idx is not None else int(returns.numel())
         gn = int(global_n) if global_n is not None else n
         st = self._stream()
         L = self._L
+        self.t += 1
+        mgn = float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0
+        prec = 1 if self.precision == 'tf32' else 0
+        log_ratio = t.empty(n, dtype=t.float32, device=self.device) if want_log_ratio else None
+        stats = t.empty(5, dtype=t.float64, device=self.device)       # loss_names order; entropy with the pre-update logstd (model.py:70)
+        ready = adv_sums is not None
+        sums = adv_sums if ready else self.adv_sums
         if self.comm is None and gn == n:          # single GPU: the whole minibatch step is one library call
-            log_ratio = t.empty(n, dtype=t.float32, device=self.device) if want_log_ratio else None
-            stats = t.empty(5, dtype=t.float64, device=self.device)
-            self.t += 1
-            mgn = float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0
             _lib.check(L.rs_ppo_minibatch_step(self._p(self.params), self._p(self.m), self._p(self.v), self.D, self.A, self._p(obs),
                                                self._p(actions), self._p(returns), self._p(values), self._p(neglogpacs), self._p(weights),
                                                self._p(idx), n, float(cliprange), self.ent_coef, self.vf_coef, mgn, float(lr), self.t,
-                                               self._p(self._workspace(n)), self._p(self.grad_stats), self._p(self.adv_sums),
-                                               self._p(self.scratch), self._p(self.gnorm), self._p(stats), self._p(log_ratio),
-                                               1 if self.precision == 'tf32' else 0, st))
+                                               self._p(self._workspace(n)), self._p(self.grad_stats), self._p(sums), 1 if ready else 0,
+                                               self._p(self.gnorm), self._p(stats), self._p(log_ratio), prec, st))
             return stats, log_ratio
-        _lib.check(L.rs_adv_moments(self._p(idx), n, self._p(returns), self._p(values), self._p(self.adv_sums), st))
-        if self.comm is not None:
-            self.comm.all_reduce_sum(self.adv_sums)
-        log_ratio = t.empty(n, dtype=t.float32, device=self.device) if want_log_ratio else None
+        if not ready:
+            _lib.check(L.rs_adv_moments(self._p(idx), n, self._p(returns), self._p(values), self._p(sums), st))
+            if self.comm is not None:
+                self.comm.all_reduce_sum(sums)
         _lib.check(L.rs_ppo_grad(self._p(self.params), self.D, self.A, self._p(obs), self._p(actions), self._p(returns), self._p(values),
-                                 self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(self.adv_sums), float(cliprange),
+                                 self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(sums), float(cliprange),
                                  self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio),
-                                 1 if self.precision == 'tf32' else 0, st))
+                                 self._p(stats), prec, st))
         if self.comm is not None:
-            self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums]: one latency-bound NCCL all-reduce
-        stats = t.empty(5, dtype=t.float64, device=self.device)         # loss_names order; entropy with the pre-update logstd (model.py:70)
-        _lib.check(L.rs_ppo_stats(self._p(self.grad_stats), self._p(self.params), self.D, self.A, gn, self._p(stats), st))
-        self.t += 1
-        mgn = float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0
+            self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums]: THE collective of a minibatch step (98 KB, latency-bound)
         _lib.check(L.rs_adam_step(self._p(self.params), self._p(self.m), self._p(self.v), self._p(self.grad_stats), self.D, self.A,
-                                  self.ent_coef, mgn, float(lr), self.t, 0.9, 0.999, 1e-5, self._p(self.scratch), self._p(self.gnorm), st))
+                                  self.ent_coef, mgn, float(lr), self.t, 0.9, 0.999, 1e-5, self._p(self.gnorm), gn, self._p(stats), st))
         return stats, log_ratio
 
     def stats_to_list(self, stats_dev):

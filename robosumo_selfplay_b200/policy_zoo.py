@@ -54,11 +54,9 @@ class ZooMLPPolicy:
     def load(cls, path, ob_dim, ac_dim, device=0):
         return cls(np.load(path), ob_dim, ac_dim, device)
 
-    def act(self, observation, stochastic=False):
-        """observation [n, D] (numpy or torch).  Returns (actions [n, A], {'vpred': [n]}) like policy.py:72-80."""
+    def mean_value(self, ob):
+        """ob [n, D] device float32 -> (mean [n, A], un-normalised value prediction [n]) (policy.py:39-70)."""
         t = self.torch
-        is_t = t.is_tensor(observation)
-        ob = observation.to(self.device, t.float32) if is_t else t.as_tensor(np.asarray(observation, dtype=np.float32), device=self.device)
         obz = t.clamp((ob - self.ob_mean) / self.ob_std, -5.0, 5.0).contiguous()
         n = obz.shape[0]
         mean = t.empty((n, self.A), dtype=t.float32, device=self.device)
@@ -68,11 +66,76 @@ class ZooMLPPolicy:
         job[0].mean = mean.data_ptr(); job[0].value = value.data_ptr(); job[0].activation = 1
         st = ctypes.c_void_p(t.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self._L.rs_mlp_forward_multi(job, 1, self.D, self.A, n, 0, st))
+        return mean, value * self.ret_std + self.ret_mean
+
+    def act(self, observation, stochastic=False):
+        """observation [n, D] (numpy or torch).  Returns (actions [n, A], {'vpred': [n]}) like policy.py:72-80."""
+        t = self.torch
+        is_t = t.is_tensor(observation)
+        ob = observation.to(self.device, t.float32) if is_t else t.as_tensor(np.asarray(observation, dtype=np.float32), device=self.device)
+        mean, vpred = self.mean_value(ob)
         act = mean + t.exp(self.logstd) * t.randn_like(mean) if stochastic else mean
-        vpred = value * self.ret_std + self.ret_mean
         if is_t:
             return act, {'vpred': vpred}
         return act.cpu().numpy(), {'vpred': vpred.cpu().numpy()}
+
+
+class _ZooActModel:
+    """PolicyWithValue surface (policies.py:84-128) over a zoo MLP for the learner-sized (D + 1)-wide observation: the timestep
+    feature this fork appends (sumo_env.py:68-70) is cut off, as eval_robosumo_against_fix.py:207 does."""
+
+    def __init__(self, zoo, seed=0):
+        self.zoo, self.torch = zoo, zoo.torch
+        self.D, self.A, self.device = zoo.D + 1, zoo.A, zoo.device
+        self.initial_state = None
+        self._seed, self._tick = seed, 0
+        self._L = zoo._L
+
+    def _mean_value(self, observation):
+        t = self.torch
+        ob = observation.to(self.device, t.float32) if t.is_tensor(observation) else t.as_tensor(np.asarray(observation, dtype=np.float32), device=self.device)
+        return self.zoo.mean_value(ob[:, :self.zoo.D])
+
+    def _nlp(self, act, mean):
+        t = self.torch
+        act = act.contiguous(); mean = mean.contiguous()
+        out = t.empty((act.shape[0],), dtype=t.float32, device=self.device)
+        st = ctypes.c_void_p(t.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self._L.rs_neglogp(act.shape[0], self.A, ctypes.c_void_p(act.data_ptr()), ctypes.c_void_p(mean.data_ptr()),
+                                      ctypes.c_void_p(self.zoo.logstd.data_ptr()), ctypes.c_void_p(out.data_ptr()), st))
+        return out
+
+    def step(self, observation, deterministic=False, **_):
+        t = self.torch
+        mean, value = self._mean_value(observation)
+        if deterministic:
+            act = mean.clone()
+        else:
+            g = t.Generator(device=self.device); g.manual_seed(self._seed * 1000003 + self._tick)
+            self._tick += 1
+            act = mean + t.exp(self.zoo.logstd) * t.randn(mean.shape, generator=g, device=self.device, dtype=t.float32)
+        return act, value, None, self._nlp(act, mean)
+
+    def value(self, ob, *a, **k):
+        return self._mean_value(ob)[1]
+
+    def action_probability(self, observation, given_action=None, **_):
+        t = self.torch
+        act = given_action.to(self.device, t.float32) if t.is_tensor(given_action) else t.as_tensor(np.asarray(given_action, dtype=np.float32), device=self.device)
+        return self._nlp(act, self._mean_value(observation)[0])
+
+
+class ZooOpponentModel:
+    """What `runner.models[1]` is under opponent_mode='fix' (alg_ppo.py:194-206): a non-trainable model whose act_model is the
+    pretrained policy_zoo MLP.  `generic = True` makes Runner step it through the step / action_probability surface instead of
+    the fused four-job MLP launch (different width, tanh units and an observation filter)."""
+    generic = True
+    trainable = False
+
+    def __init__(self, zoo, seed=0):
+        self.act_model = _ZooActModel(zoo, seed)
+        self.D, self.A, self.device = self.act_model.D, zoo.A, zoo.device
+        self.step, self.value, self.initial_state = self.act_model.step, self.act_model.value, None
 
 
 def evaluate_against_fixed(env, model, opponent, rounds, max_steps=100000):

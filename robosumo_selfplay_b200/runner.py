@@ -78,8 +78,29 @@ class Runner:
         mb_shaping = t.empty((2, T, E), **f32); mb_main = t.empty((2, T, E), **f32)
         ep_done = t.empty((T, E), dtype=t.uint8, device=dev); ep_info = t.empty((T, E, 3), **f32)
         m0, m1 = self.models[0].act_model, self.models[1].act_model
-        ls0, ls1 = m0.logstd().contiguous(), m1.logstd().contiguous()
+        generic = bool(getattr(self.models[1], 'generic', False))      # opponent_mode='fix': a policy_zoo MLP behind the step / action_probability surface
         host_epinfos = []
+        if generic:
+            assert self.device_env, "a generic opponent needs the device-style env"
+            for step in range(T):
+                o0, o1 = self.obs[:, 0, :], self.obs[:, 1, :]
+                a0, v0, _, nlp0 = m0.step(o0, deterministic=deterministic)                       # runner.py:67
+                opp0 = m1.action_probability(o0, given_action=a0)                                # runner.py:85
+                a1, _, _, opp1 = m1.step(o1, deterministic=deterministic)                        # runner.py:67 (agent 1)
+                v01, nlp1 = m0.value_and_neglogp(o1, given_action=a1)                            # runner.py:89-90
+                mb_obs[0, step].copy_(o0); mb_obs[1, step].copy_(o1)
+                mb_dones[:, step].copy_(self.dones.t())
+                mb_values[0, step].copy_(v0); mb_values[1, step].copy_(v01)
+                mb_nlp[0, step].copy_(nlp0); mb_nlp[1, step].copy_(nlp1)
+                mb_opp_nlp[0, step].copy_(opp0); mb_opp_nlp[1, step].copy_(opp1)
+                mb_actions[step, :, 0].copy_(a0); mb_actions[step, :, 1].copy_(a1)
+                obs, rew, done, (info, epi) = self.env.step(mb_actions[step])
+                self.obs.copy_(obs); self.dones.copy_(done)
+                mb_shaping[:, step].copy_(info[:, :, 6].t()); mb_main[:, step].copy_(info[:, :, 3].t())
+                ep_done[step].copy_(done[:, 0]); ep_info[step].copy_(epi)
+            return self._finish(update, as_numpy, m0, mb_obs, mb_actions, mb_values, mb_nlp, mb_opp_nlp, mb_dones, mb_shaping, mb_main, ep_done,
+                                ep_info, host_epinfos)
+        ls0, ls1 = m0.logstd().contiguous(), m1.logstd().contiguous()
         mu00 = t.empty((E, A), **f32); mu10 = t.empty((E, A), **f32); mu11 = t.empty((E, A), **f32); mu01 = t.empty((E, A), **f32)
         v00 = t.empty((E,), **f32); v01 = t.empty((E,), **f32)
         jobs = (_lib.rs_mlp_job * 4)()
@@ -130,17 +151,30 @@ class Runner:
             else:   # any gym-style VecEnv with the reference's numpy surface
                 obs, rew, done, infos = self.env.step(act.cpu().numpy())
                 self.obs.copy_(self._to_dev(obs)); self.dones.copy_(self._to_dev(np.asarray(done), t.uint8))
-                if 'shaping_reward' in infos[0][0]:
+                if hasattr(infos, 'column'):          # LazyInfos of the host-style B200SumoVecEnv: whole columns, no per-env dicts
+                    sh = infos.column('shaping_reward').T; mn = infos.column('main_reward').T
+                    fin = infos.finished()
+                elif 'shaping_reward' in infos[0][0]:
                     sh = np.array([[infos[e][a]['shaping_reward'] for e in range(E)] for a in range(2)])
                     mn = np.array([[infos[e][a]['main_reward'] for e in range(E)] for a in range(2)])
+                    fin = range(E)
                 else:
                     sh = np.asarray(rew, dtype=np.float64).T; mn = sh
+                    fin = range(E)
                 mb_shaping[:, step].copy_(self._to_dev(sh)); mb_main[:, step].copy_(self._to_dev(mn))
                 ep_done[step].zero_()
-                for e in range(E):
+                for e in fin:
                     ei = infos[e][0].get('episode')
                     if ei:
                         host_epinfos.append(ei)
+        return self._finish(update, as_numpy, m0, mb_obs, mb_actions, mb_values, mb_nlp, mb_opp_nlp, mb_dones, mb_shaping, mb_main, ep_done,
+                            ep_info, host_epinfos)
+
+    def _finish(self, update, as_numpy, m0, mb_obs, mb_actions, mb_values, mb_nlp, mb_opp_nlp, mb_dones, mb_shaping, mb_main, ep_done, ep_info,
+                host_epinfos):
+        """Bootstrap values, reward curriculum + IS ratios + V-trace, episode records and the sf01 flattening (runner.py:127-252)."""
+        t = self.torch
+        T, E = self.nsteps, self.nenv
         last_values = t.stack([m0.forward(self.obs[:, a, :], want_mean=False)[1] for a in range(2)])     # runner.py:184
         out = self.postprocess(update, mb_shaping, mb_main, mb_values, mb_nlp, mb_opp_nlp, mb_dones, last_values, self.dones)
         rewards, returns, ratios = out

@@ -113,6 +113,50 @@ class _AgentView:
         self.action_dim = spec.nu
 
 
+class LazyInfos:
+    """Sequence of E entries; entry e = (info dict of agent 0, info dict of agent 1), built when indexed."""
+
+    def __init__(self, info, done, epi, t):
+        self._info, self._done, self._epi, self._t = info, done, epi, t
+
+    def __len__(self):
+        return self._info.shape[0]
+
+    def __getitem__(self, e):
+        if isinstance(e, slice):
+            return tuple(self[i] for i in range(*e.indices(len(self))))
+        if e < 0:
+            e += len(self)
+        if not 0 <= e < len(self):
+            raise IndexError(e)
+        pair = []
+        for a in range(2):
+            row = self._info[e, a]
+            d = {k: float(row[i]) for i, k in enumerate(INFO_KEYS)}
+            flags = int(row[7])
+            if flags & 1:
+                d['winner'] = True
+            if flags & 2:
+                d['timeout'] = True
+            if a == 0 and self._done[e, 0]:
+                d['episode'] = {'r': round(float(self._epi[e, 0]), 6), 'dr': round(float(self._epi[e, 1]), 6),
+                                'l': int(self._epi[e, 2]), 't': self._t}
+            pair.append(d)
+        return tuple(pair)
+
+    def __iter__(self):
+        return (self[e] for e in range(len(self)))
+
+    # vectorised accessors for consumers that want a column without E dict constructions
+    def column(self, key):
+        """[E, 2] array of one info key (e.g. 'shaping_reward')."""
+        return self._info[:, :, INFO_KEYS.index(key)].astype(np.float64)
+
+    def finished(self):
+        """Indices of the envs whose episode ended this step (agent 0 done)."""
+        return np.nonzero(self._done[:, 0])[0]
+
+
 class B200SumoVecEnv(VecEnv):
     def __init__(self, env_id='RoboSumo-Ant-vs-Ant-v0', num_envs=8, seed=42, device=0, adjust_z=0.0,
                  device_api=False, auto_reset=True, newton_iters=16, timestep_limit=TIMESTEP_LIMIT):
@@ -232,26 +276,11 @@ class B200SumoVecEnv(VecEnv):
                 self._infos_as_dicts())
 
     def _infos_as_dicts(self):
-        """The reference's infos: tuple[E] of tuple[2] of dict (sumo.py:131-186, sumo_env.py:48-65)."""
-        out = []
-        info, done, epi = self.h_info, self.h_done, self.h_epi
-        t = round(time.time() - self.tstart, 6)
-        for e in range(self.num_envs):
-            pair = []
-            for a in range(2):
-                row = info[e, a]
-                d = {k: float(row[i]) for i, k in enumerate(INFO_KEYS)}
-                flags = int(row[7])
-                if flags & 1:
-                    d['winner'] = True
-                if flags & 2:
-                    d['timeout'] = True
-                if a == 0 and done[e, 0]:
-                    d['episode'] = {'r': round(float(epi[e, 0]), 6), 'dr': round(float(epi[e, 1]), 6),
-                                    'l': int(epi[e, 2]), 't': t}
-                pair.append(d)
-            out.append(tuple(pair))
-        return tuple(out)
+        """The reference's infos: tuple[E] of tuple[2] of dict (sumo.py:131-186, sumo_env.py:48-65) -- built LAZILY: the step
+        returns a sequence view over a snapshot of the info / done / episode arrays and `infos[e]` materialises that env's two
+        dicts on access, so the O(E) Python loop of round 1 (2 E dicts per step, several ms at E = 4096) leaves the step.
+        Runner-style consumers that only read `infos[e][a]['shaping_reward']` or scan for 'episode' work unchanged."""
+        return LazyInfos(self.h_info.copy(), self.h_done.copy(), self.h_epi.copy(), round(time.time() - self.tstart, 6))
 
     # ---- state access (parity hooks; MjSim.get_state / set_state) -------------------------
     def set_state(self, qpos, qvel):
@@ -295,15 +324,34 @@ class B200SumoVecEnv(VecEnv):
         _lib.check(self._L.rs_get_diag(self._h, ctypes.c_void_p(out.data_ptr()), self._stream()))
         return out
 
-    def check_status(self):
-        """Raise like mujoco-py's warning callback does (builder.py:351-369) if any env went bad."""
-        _, _, _, status = self.get_state()
-        bad = (status & 1).nonzero()
-        if bad.numel():
-            raise RuntimeError("B200SumoVecEnv: NaN/Inf in the state of envs %s" % bad.flatten().tolist()[:8])
+    def check_status(self, strict=True, clear=True):
+        """What mujoco-py's warning callback does inside the worker (builder.py:351-369: any MuJoCo warning becomes a
+        MujocoException), checked once per rollout on a device-side latch that auto-reset does not clear: raises on NaN/Inf state
+        (mjWARN_BADQPOS/QVEL/QACC) and, when `strict`, on a full contact buffer (mjWARN_CONTACTFULL: contacts beyond the per-pair
+        capacity were dropped).  A Newton solve that hit its iteration cap is reported as a warning (MuJoCo does not warn there).
+        Returns (bits, env_steps_flagged)."""
+        import warnings
+        out = (ctypes.c_int * 2)()
+        _lib.check(self._L.rs_status_latch(self._h, out, 1 if clear else 0, self._stream()))
+        bits, n = int(out[0]), int(out[1])
+        if bits & 1:
+            raise RuntimeError("B200SumoVecEnv: NaN/Inf in the physics state of an env pair (%d env-steps flagged since the last check)" % n)
+        if bits & 2:
+            msg = "B200SumoVecEnv: contact buffer full, contacts were dropped (%d env-steps flagged since the last check)" % n
+            if strict:
+                raise RuntimeError(msg)
+            warnings.warn(msg)
+        if bits & 4:
+            warnings.warn("B200SumoVecEnv: a constraint solve stopped at the iteration cap (%d env-steps flagged since the last check)" % n)
+        return bits, n
 
-    def seed(self, seed):
-        raise NotImplementedError("the Philox key is fixed at construction (seed=...)")
+    def seed(self, seed=None):
+        """env.seed(s) of the reference (run.py:73-83 seeds env i with seed + i; mujoco_env.py:82-84).  Here env e draws its reset
+        states from the Philox stream (seed, e); the new key takes effect at the next reset / auto-reset."""
+        if seed is None:
+            seed = int(time.time() * 1e6) & 0xFFFFFFFF
+        _lib.check(self._L.rs_seed(self._h, ctypes.c_ulonglong(int(seed) & 0xFFFFFFFFFFFFFFFF)))
+        return [int(seed) + e for e in range(self.num_envs)]
 
     def close_extras(self):
         if getattr(self, '_h', None):

@@ -340,7 +340,7 @@ def test_full_size_vtrace_and_gradient_properties():
         _lib.check(L.rs_adv_moments(p(idx), nb, p(retn), p(val), p(m.adv_sums), None))
         def grad(ix):
             _lib.check(L.rs_ppo_grad(p(m.params), D_, A_, p(obs), p(act), p(retn), p(val), p(old), None, p(ix), ix.numel(), nb, p(m.adv_sums), 0.2, 0.0, 0.5,
-                                     p(ws), p(m.grad_stats), None, 1 if precision == 'tf32' else 0, None))
+                                     p(ws), p(m.grad_stats), None, None, 1 if precision == 'tf32' else 0, None))
             torch.cuda.synchronize()
             return m.grad_stats[:m.P + 4].double().clone()
         full = grad(idx)
