@@ -145,8 +145,8 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
                 const float* values, const float* old_nlp, const float* weights, const int* idx, int n, long long global_n,
                 const double* adv_sums, float cliprange, float ent_coef, float vf_coef, float* workspace, float* grad_stats,
                 float* log_ratio, double* stats5, int precision, void* stream);
-/* entropy term, global-norm clip (model.py:130-132) and TF-style Adam (model.py:121,139) on the (all-reduced) gradient in ONE
- * launch; stats5 (may be NULL) receives [pg_loss, vf_loss, ., approxkl, clipfrac] = stat sums / global_n */
+/* global-norm clip (model.py:130-132) and TF-style Adam (model.py:121,139) on the (all-reduced) gradient in ONE launch (the
+ * entropy term is added by rs_ppo_grad: each rank its share n / global_n of it; ent_coef here is unused, kept for the signature); stats5 (may be NULL) receives [pg_loss, vf_loss, ., approxkl, clipfrac] = stat sums / global_n */
 int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
                  float lr, long long step_t, float beta1, float beta2, float eps, float* gnorm_out, long long global_n, double* stats5,
                  void* stream);

@@ -661,7 +661,7 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
     const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) {      // this rank holds no sample of the minibatch: zero contribution (the entropy still comes from the parameters)
-        rsl::k_grad_reduce2<<<(L.P + 255) / 256, 256, 0, st>>>(workspace, workspace, 0, L.P, grad_stats, params, L.logstd, act_dim, stats5);
+        rsl::k_grad_reduce2<<<(L.P + 255) / 256, 256, 0, st>>>(workspace, workspace, 0, L.P, grad_stats, params, L.logstd, act_dim, 0.f, stats5);
         g_launches++;
         CUDA_OK(cudaGetLastError());
         return RS_OK;
@@ -683,13 +683,14 @@ int rs_ppo_grad(const float* params, int obs_dim, int act_dim, const float* obs,
     a.gpart = workspace; a.spart = workspace + (size_t)nb * L.P; a.log_ratio = log_ratio;
     if (precision == 1) rsl::k_ppo_tile_tc<<<nb, RSL_TC_THREADS, sm, st>>>(a);
     else rsl::k_ppo_tile<<<nb, RSL_TILE, sm, st>>>(a);
-    rsl::k_grad_reduce2<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, params, L.logstd, act_dim, stats5);
+    rsl::k_grad_reduce2<<<(L.P + 255) / 256, 256, 0, st>>>(a.gpart, a.spart, nb, L.P, grad_stats, params, L.logstd, act_dim,
+                                                          (float)((double)ent_coef * (double)n / (double)global_n), stats5);
     g_launches += 2;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
 }
 
-/* entropy term, global-norm clip and TF-style Adam on the (all-reduced) gradient, ONE launch; also finalises the statistics
+/* global-norm clip and TF-style Adam on the (all-reduced) gradient (entropy term already in it, see rs_ppo_grad), ONE launch; also finalises the statistics
  * [pg_loss, vf_loss, ., approxkl, clipfrac] from the stat sums behind the gradient when stats5 != NULL.  step_t counts from 1. */
 int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, int act_dim, float ent_coef, float max_grad_norm,
                  float lr, long long step_t, float beta1, float beta2, float eps, float* gnorm_out, long long global_n, double* stats5,
@@ -698,7 +699,7 @@ int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, in
     const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
     cudaStream_t st = (cudaStream_t)stream;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step_t)) / (1.0 - pow((double)beta1, (double)step_t));
-    rsl::k_adam2<<<(L.P + 255) / 256, 256, 0, st>>>(params, m, v, grad, L.P, ent_coef, act_dim, L.logstd, max_grad_norm, (float)lr_t, beta1, beta2, eps,
+    rsl::k_adam2<<<(L.P + 255) / 256, 256, 0, st>>>(params, m, v, grad, L.P, max_grad_norm, (float)lr_t, beta1, beta2, eps,
                                                     gnorm_out, stats5 ? 1.0 / (double)global_n : 0.0, stats5);
     g_launches += 1;
     CUDA_OK(cudaGetLastError());

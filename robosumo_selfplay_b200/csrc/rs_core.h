@@ -1231,11 +1231,18 @@ RS_HD float line_search(Ctx<LA, LB>& c) {
     RS_UNROLL1
     for (int o = 16; o; o >>= 1) { lo = fmaxf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fminf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
 #endif
-    const float am = hi < 1.0e38f ? 0.5f * (lo + hi) : 2.f * fmaxf(lo, 0.5f);      // inside the linear piece that holds the root
+    // a point inside the linear piece (lo, hi) that holds the root, as close to lo as is safely past that breakpoint: the Newton
+    // step from it is exact, and evaluating near the small end keeps am - d1 / d2 free of cancellation when hi is astronomically
+    // large (a row with a tiny jd puts a breakpoint at 1e9)
+    const float am = lo + fminf(0.5f * (hi - lo), 1e-3f * fmaxf(lo, 1.f));
     float d1, d2;
     dphi(c, am, p0, p1, &d1, &d2);
     float alpha = am - RS_DIV(d1, d2);
     alpha = fminf(fmaxf(alpha, lo), hi);
+#ifdef RS_LS_DEBUG
+    { float e1, e2; dphi(c, alpha, p0, p1, &e1, &e2); float z1, z2; dphi(c, 0.f, p0, p1, &z1, &z2);
+      printf("  ls: R %d p0 %g p1 %g phi'(0) %g lo %g hi %g am %g d1 %g d2 %g alpha %g phi'(alpha) %g\n", R, p0, p1, z1, lo, hi, am, d1, d2, alpha, e1); }
+#endif
     return alpha;
 }
 
@@ -1340,6 +1347,9 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
     }
     float alpha = 1.f;
     if (!same && !predicted) alpha = line_search(c);
+#ifdef RS_LS_DEBUG
+    printf(" iter: same %d predicted %d alpha %g ncon %d coupled %d\n", same, predicted, alpha, s.ncon, s.coupled);
+#endif
     if (same) { RS_LANE_LOOP(i, S::NV) { s.x[i] += s.d[i]; } }       // converged: r is not needed any more, M d was never formed
     else { RS_LANE_LOOP(i, S::NV) { s.x[i] += alpha * s.d[i]; s.r[i] += alpha * s.Md[i]; } }
     RS_LANE_LOOP(k, s.ncon) {

@@ -560,15 +560,19 @@ __global__ void __launch_bounds__(1024) k_adv_moments_multi(const int* __restric
 // ---- fused minibatch epilogue: two launches instead of four --------------------------------------------------------------------
 // (1) per-block partials -> grad_stats [P + 4] in block order (deterministic) and, by block 0, the entropy of the PRE-update
 //     parameters into stats5[2] (model.py:137 evaluates it in the same session.run as the train op);
-// (2) after the data-parallel all-reduce (if any): entropy term, global norm, clip, TF-style Adam and the other four statistics.
+// (2) after the data-parallel all-reduce (if any): global norm, clip, TF-style Adam and the other four statistics.
 //     Every block recomputes the sum of squares over the whole gradient in the same fixed order (24.5 k numbers: cheaper than a
 //     separate single-block launch plus its launch gap, and deterministic).
 __global__ void k_grad_reduce2(const float* __restrict__ gpart, const float* __restrict__ spart, int nblocks, int P,
-                               float* __restrict__ grad, const float* __restrict__ params, int logstd_off, int A, double* __restrict__ stats5) {
+                               float* __restrict__ grad, const float* __restrict__ params, int logstd_off, int A, float ent_share,
+                               double* __restrict__ stats5) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P) {
         float s = 0.f;
         for (int b = 0; b < nblocks; b++) s += gpart[(size_t)b * P + i];
+        // - ent_coef * d entropy / d logstd (= 1 per component): this rank's share n_local / n_global of it, so that the all-reduced
+        // gradient carries the term exactly once and grad_stats is the final gradient on one GPU
+        if (i >= logstd_off && i < logstd_off + A) s -= ent_share;
         grad[i] = s;
     }
     if (blockIdx.x == 0 && threadIdx.x < 4) {
@@ -583,15 +587,11 @@ __global__ void k_grad_reduce2(const float* __restrict__ gpart, const float* __r
     }
 }
 __global__ void __launch_bounds__(256) k_adam2(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, float* __restrict__ grad,
-                                               int P, float ent_coef, int A, int logstd_off, float max_grad_norm, float lr_t, float b1, float b2,
+                                               int P, float max_grad_norm, float lr_t, float b1, float b2,
                                                float eps, float* __restrict__ gnorm_out, double inv_n, double* __restrict__ stats5) {
     __shared__ double sh[8];
     double sq = 0;
-    for (int j = threadIdx.x; j < P; j += blockDim.x) {
-        float g = grad[j];
-        if (j >= logstd_off && j < logstd_off + A) g -= ent_coef;                      // - ent_coef * d entropy / d logstd
-        sq += (double)g * (double)g;
-    }
+    for (int j = threadIdx.x; j < P; j += blockDim.x) { const float g = grad[j]; sq += (double)g * (double)g; }
     for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
     __syncthreads();
@@ -606,9 +606,7 @@ __global__ void __launch_bounds__(256) k_adam2(float* __restrict__ params, float
         if (stats5) { stats5[0] = (double)grad[P] * inv_n; stats5[1] = (double)grad[P + 1] * inv_n; stats5[3] = (double)grad[P + 2] * inv_n; stats5[4] = (double)grad[P + 3] * inv_n; }
     }
     if (i >= P) return;
-    float g0 = grad[i];
-    if (i >= logstd_off && i < logstd_off + A) { g0 -= ent_coef; }
-    const float g = g0 * scale;
+    const float g = grad[i] * scale;
     const float mi = b1 * m[i] + (1.f - b1) * g;
     const float vi = b2 * v[i] + (1.f - b2) * g * g;
     m[i] = mi; v[i] = vi;

@@ -108,3 +108,28 @@ def test_trajectory_mixed_morphology_pairs(na, nb, emu):
         om.step(q, v, ctrl, 5, w)
         st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 8, P(qf), P(vf), P(wf), P(ctrl.astype(np.float32)), 5)
         assert st == 0 and abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3, t
+
+
+def test_line_search_regression_cases_and_no_iteration_cap(emu, oracle_models):
+    """States (tests/golden/newton_linesearch_cases.npz, found by a soak of the host emulation) where a row with a tiny J.d puts a
+    line-search breakpoint at alpha ~ 1e9: the one-pass exact line search must evaluate phi' near the SMALL end of the bracketing
+    linear piece (a midpoint there loses the root to cancellation and the solver then stalls at the iteration cap).  The step must
+    converge (status 0) and agree with the float64 oracle; a short soak must never raise RS_STATUS_NEWTON_MAXIT."""
+    import os
+    om = oracle_models('ant'); ps = PairSpec('ant', 'ant')
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'newton_linesearch_cases.npz'))
+    for q0, v0, w0, ctrl in zip(z['q'], z['v'], z['w'], z['ctrl']):
+        qf, vf, wf = q0.copy(), v0.copy(), w0.copy()
+        st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 16, P(qf), P(vf), P(wf), P(ctrl), 5)
+        assert st == 0
+        q, v, w = q0.astype(np.float64), v0.astype(np.float64), w0.astype(np.float64)
+        om.normalize_qpos(q)
+        om.step(q, v, ctrl.astype(np.float64), 5, w)
+        assert abs(q - qf).max() < 2e-4 and abs(v - vf).max() < 5e-3
+    rng = np.random.RandomState(11)
+    for env in range(25):
+        q, v = reset_like_state(om, rng)
+        qf, vf, wf = q.astype(np.float32), v.astype(np.float32), np.zeros(om.nv, np.float32)
+        for t in range(100):
+            st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 16, P(qf), P(vf), P(wf), P(rng.randn(om.nu).astype(np.float32)), 5)
+            assert st & 5 == 0, (env, t, st)
