@@ -160,20 +160,21 @@ class SnapshotRing:
     def __init__(self, P, device, capacity=64):
         import torch
         self.torch, self.P, self.device = torch, P, device
-        self.buf = torch.empty((capacity, P), dtype=torch.float32, device=device)
+        self.stride = (P + 31) & ~31                    # rows are read in place by kernels that issue 16-byte loads: keep them 128-byte aligned
+        self.buf = torch.empty((capacity, self.stride), dtype=torch.float32, device=device)
         self.row = {}                                   # version -> row
 
     def put(self, version, params):
         if version not in self.row:
             if len(self.row) == self.buf.shape[0]:
-                nb = self.torch.empty((2 * self.buf.shape[0], self.P), dtype=self.torch.float32, device=self.device)
+                nb = self.torch.empty((2 * self.buf.shape[0], self.stride), dtype=self.torch.float32, device=self.device)
                 nb[:self.buf.shape[0]].copy_(self.buf)
                 self.buf = nb
             self.row[version] = len(self.row)
-        self.buf[self.row[version]].copy_(params)
+        self.buf[self.row[version], :self.P].copy_(params)
 
     def get(self, version):
-        return self.buf[self.row[version]]
+        return self.buf[self.row[version], :self.P]
 
     def versions(self):
         return sorted(self.row)
