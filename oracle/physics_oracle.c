@@ -14,9 +14,11 @@
  * reference holds no golden trajectory for this path; the algorithm below follows
  * MuJoCo's published computation (soft constraints with solref/solimp impedance,
  * pyramidal friction cones, primal Newton solver on the convex cost, RK4 with a full
- * forward evaluation per stage).  Simplifications, shared with the CUDA path and
- * documented in DESIGN.md: capsule/sphere-vs-box uses endpoint-sphere tests; the thin
- * border cylinders are treated as capsules (MuJoCo uses MPR for those pairs).
+ * forward evaluation per stage).  Narrow phase, shared with the CUDA path and documented in
+ * capsule-vs-box = the two endpoint spheres plus the closest box edge against the
+ * capsule interior (exact distance outside the box; MuJoCo's mjc_CapsuleBox emits its own
+ * multi-contact set); the thin border cylinders are treated as capsules (MuJoCo uses its
+ * convex-convex routine for those pairs; they differ at the cylinders' flat ends only).
  *
  * Formulation is deliberately different from the CUDA kernels (generic body tree,
  * explicit per-body Jacobians, dense matrices) so that agreement is evidence.
@@ -414,6 +416,43 @@ static void sphere_box(Data* d, const Model* m, int gs, int gb, const double* c,
     for (int k = 0; k < 3; k++) { pos[k] += bp[k]; n[k] = -n[k]; }   /* from sphere (geom1) to box (geom2) */
     add_con(d, gs, gb, dist, pos, n, NULL, margin);
 }
+/* Capsule INTERIOR against the box edges.  The distance from a segment to a convex box is attained at a segment endpoint (the two
+ * endpoint-sphere tests) or, with an interior point of the segment, on a box EDGE; so those two plus this test give the exact
+ * distance whenever the axis is outside the box (a leg straddling the tatami edge, tatami.xml:21, utils.py:64-68).  At most one
+ * contact: the closest edge.  [M] MuJoCo's own mjc_CapsuleBox is a different multi-contact routine; see DESIGN.md section 4. */
+static void capsule_box_edges(Data* d, const Model* m, int gc, int gb, double margin) {
+    const double* bp = d->gpos + 3*gb; const double* R = d->gmat + 9*gb; const double* h = m->geom_size + 3*gb;
+    const double* cp = d->gpos + 3*gc; const double* Rc = d->gmat + 9*gc;
+    double r = m->geom_size[3*gc], l1 = m->geom_size[3*gc + 1];
+    double diff[3] = { cp[0]-bp[0], cp[1]-bp[1], cp[2]-bp[2] }, p1[3], a1w[3] = { Rc[2], Rc[5], Rc[8] }, a1[3];
+    matT_vec(p1, R, diff); matT_vec(a1, R, a1w);                 /* capsule centre and axis in the box frame */
+    double best = 1e300, bpg[3] = {0, 0, 0}, bpe[3] = {0, 0, 0};
+    for (int ax = 0; ax < 3; ax++) for (int s1 = -1; s1 <= 1; s1 += 2) for (int s2 = -1; s2 <= 1; s2 += 2) {
+        int u = (ax + 1) % 3, w = (ax + 2) % 3;
+        double p2[3] = {0, 0, 0}, a2[3] = {0, 0, 0}, l2 = h[ax];
+        p2[u] = s1 * h[u]; p2[w] = s2 * h[w]; a2[ax] = 1.0;
+        double dif[3] = { p1[0]-p2[0], p1[1]-p2[1], p1[2]-p2[2] };
+        double mb = -dot3(a1, a2), uu = -dot3(a1, dif), vv = dot3(a2, dif), det = 1.0 - mb*mb, x1, x2;
+        if (fabs(det) < 1e-12) continue;                        /* parallel: the endpoint tests cover it */
+        x1 = (uu - mb*vv) / det; x2 = (vv - mb*uu) / det;
+        if (x1 > l1) { x1 = l1; x2 = vv - mb*l1; } else if (x1 < -l1) { x1 = -l1; x2 = vv + mb*l1; }
+        if (x2 > l2) { x2 = l2; x1 = uu - mb*l2; } else if (x2 < -l2) { x2 = -l2; x1 = uu + mb*l2; }
+        if (x1 > l1) x1 = l1; else if (x1 < -l1) x1 = -l1;
+        if (fabs(x1) >= l1 * (1.0 - 1e-6)) continue;            /* an endpoint is closest: already tested as a sphere */
+        double pg[3], pe[3];
+        for (int k = 0; k < 3; k++) { pg[k] = p1[k] + a1[k]*x1; pe[k] = p2[k] + a2[k]*x2; }
+        if (fabs(pg[0]) < h[0] && fabs(pg[1]) < h[1] && fabs(pg[2]) < h[2]) continue;   /* axis point inside the box: face push-out case */
+        double dd[3] = { pg[0]-pe[0], pg[1]-pe[1], pg[2]-pe[2] }, len = sqrt(dot3(dd, dd));
+        if (len - r < best) { best = len - r; memcpy(bpg, pg, 24); memcpy(bpe, pe, 24); }
+    }
+    if (best >= margin) return;
+    double nl[3] = { bpe[0]-bpg[0], bpe[1]-bpg[1], bpe[2]-bpg[2] }, posl[3], n[3], pos[3];   /* from capsule (geom1) to box (geom2) */
+    if (normalize3(nl) < 1e-12) return;
+    for (int k = 0; k < 3; k++) posl[k] = bpe[k] - nl[k]*0.5*best;
+    mat_vec(n, R, nl); mat_vec(pos, R, posl);
+    for (int k = 0; k < 3; k++) pos[k] += bp[k];
+    add_con(d, gc, gb, best, pos, n, NULL, margin);
+}
 static void cap_ends(const Data* d, const Model* m, int g, double* e0, double* e1) {
     const double* p = d->gpos + 3*g; const double* R = d->gmat + 9*g; double h = m->geom_size[3*g + 1];
     for (int k = 0; k < 3; k++) { e0[k] = p[k] + R[3*k + 2]*h; e1[k] = p[k] - R[3*k + 2]*h; }
@@ -442,6 +481,7 @@ static void collide_pair(const Model* m, Data* d, int ga, int gb) {
     else if (t1 == G_CAPSULE && t2 == G_BOX) {
         cap_ends(d, m, g1, e0, e1);
         sphere_box(d, m, g1, g2, e0, r1, margin); sphere_box(d, m, g1, g2, e1, r1, margin);
+        capsule_box_edges(d, m, g1, g2, margin);
     }
 }
 

@@ -502,6 +502,35 @@ RS_HD void collide(Ctx<LA, LB>& c) {
         // keys: geom i owns 12 slots: end0 {floor, box}, end1 {floor, box}, rails 4..7; pair contacts start at 12 * NG
         sphere_vs_world(c, body, e0, r, iw, ax, 12 * i, true);
         if (!sph) sphere_vs_world(c, body, e1, r, iw, ax, 12 * i + 2, true);
+        // capsule INTERIOR against the tatami's top and vertical edges (the distance from a segment to the box is attained at an
+        // endpoint -- the sphere tests above -- or on an edge): a leg straddling the edge at |x| = 2.3 rests on it instead of
+        // sinking through until an endpoint touches.  At most one contact (the closest edge), key slot 8.
+        if (!sph && (fmaxf(fabsf(e0.x), fabsf(e1.x)) + r + RS_MARGIN >= RS_BOX_HX || fmaxf(fabsf(e0.y), fabsf(e1.y)) + r + RS_MARGIN >= RS_BOX_HX)
+            && fminf(e0.z, e1.z) - r - RS_MARGIN < RS_BOX_CZ + RS_BOX_HZ) {
+            const V3 pc = 0.5f * (e0 + e1);
+            const float hl = 0.5f * len;
+            float best = 1e30f; V3 bg = pc, be = pc;
+            RS_UNROLL1
+            for (int k = 0; k < 8; k++) {
+                // k < 4: top edges (y = +-HX along x, x = +-HX along y at z = top); k >= 4: the four vertical edges
+                V3 ep, ea; float el;
+                if (k < 4) { const float sg = (k & 2) ? -1.f : 1.f; ep = (k & 1) ? v3(sg * RS_BOX_HX, 0.f, RS_BOX_CZ + RS_BOX_HZ) : v3(0.f, sg * RS_BOX_HX, RS_BOX_CZ + RS_BOX_HZ);
+                             ea = (k & 1) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f); el = RS_BOX_HX; }
+                else { ep = v3((k & 1) ? RS_BOX_HX : -RS_BOX_HX, (k & 2) ? RS_BOX_HX : -RS_BOX_HX, RS_BOX_CZ); ea = v3(0.f, 0.f, 1.f); el = RS_BOX_HZ; }
+                if (fabsf(dot(ax, ea)) > 1.f - 1e-6f) continue;            // parallel: the endpoint tests cover it
+                V3 pg, pe;
+                seg_seg(pc, ax, hl, ep, ea, el, &pg, &pe);
+                if (fabsf(dot(pg - pc, ax)) >= hl * (1.f - 1e-6f)) continue;   // an endpoint is closest
+                if (fabsf(pg.x) < RS_BOX_HX && fabsf(pg.y) < RS_BOX_HX && fabsf(pg.z - RS_BOX_CZ) < RS_BOX_HZ) continue;   // inside: face push-out case
+                const float dd = norm(pg - pe) - r;
+                if (dd < best) { best = dd; bg = pg; be = pe; }
+            }
+            if (best < RS_MARGIN) {
+                float l2;
+                const V3 n = normalized(bg - be, &l2);                    // from the box to the capsule
+                if (l2 > 1e-12f) add_contact(c, -1, body, best, be + (0.5f * best) * n, n, v3(0, 0, 0), iw, 12 * i + 8);
+            }
+        }
         // rails (thin cylinders treated as capsules of radius RS_RAIL_R)
         float mx = fmaxf(fabsf(e0.x), fabsf(e1.x)) + r + RS_MARGIN + RS_RAIL_R;
         float my = fmaxf(fabsf(e0.y), fabsf(e1.y)) + r + RS_MARGIN + RS_RAIL_R;

@@ -133,3 +133,31 @@ def test_line_search_regression_cases_and_no_iteration_cap(emu, oracle_models):
         for t in range(100):
             st = emu.emu_step(ps.pack(), ctypes.c_float(0.01), 16, P(qf), P(vf), P(wf), P(rng.randn(om.nu).astype(np.float32)), 5)
             assert st & 5 == 0, (env, t, st)
+
+
+def test_leg_straddling_the_tatami_edge(emu, oracle_models):
+    """Arena geometry at the box edge, |x| in [2.1, 2.3] (tatami.xml:21, utils.py:64-68): agent 0 hangs over the edge in random
+    poses, so that legs cross it with neither endpoint touching.  Kernel source and oracle must find the same contacts (endpoint
+    spheres + the closest edge against the capsule interior) and the same accelerations; at least some poses must produce a
+    contact ON the edge whose normal is neither vertical nor horizontal (i.e. an edge, not a face, contact)."""
+    om = oracle_models('ant'); ps = PairSpec('ant', 'ant')
+    rng = np.random.RandomState(0)
+    n_edge = n_checked = 0
+    for trial in range(300):
+        q = om.qpos0.copy()
+        q[0:3] = [rng.uniform(1.7, 2.2), rng.uniform(-1, 1), rng.uniform(0.6, 1.0)]
+        quat = rng.randn(4) * [1, .3, .3, .5]; q[3:7] = quat / np.linalg.norm(quat)
+        q[7:15] += rng.uniform(-.5, .5, 8)
+        q[15:18] = [-1.0, 0, 0.9]                 # agent 1 well clear of the mat
+        v = 0.1 * rng.randn(om.nv); ctrl = rng.uniform(-1, 1, om.nu)
+        om.normalize_qpos(q)
+        r = om.forward(q, v, ctrl, full=True)
+        edge = [c for c in r['contacts'] if abs(abs(c[1]) - 2.3) < 0.02 and abs(c[3] - 0.5) < 0.05 and 0.05 < abs(c[6]) < 0.98]
+        if not edge:
+            continue
+        n_edge += 1
+        qacc, M, ncon, nit, st = emu_forward(emu, ps, q, v, ctrl)
+        assert ncon == r['ncon'] and st == 0, (trial, ncon, r['ncon'])
+        assert abs(qacc - r['qacc']).max() <= 3e-4 * max(1.0, abs(r['qacc']).max()), trial
+        n_checked += 1
+    assert n_edge >= 10 and n_checked == n_edge
