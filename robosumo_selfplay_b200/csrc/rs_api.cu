@@ -345,7 +345,8 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     d.P.init_pos_noise = cfg->init_pos_noise; d.P.init_vel_noise = cfg->init_vel_noise;
     d.P.seed_lo = (uint32_t)cfg->seed; d.P.seed_hi = (uint32_t)(cfg->seed >> 32);
     CUDA_OK(cudaMalloc(&d.qpos, sizeof(float) * E * h->nq)); CUDA_OK(cudaMalloc(&d.qvel, sizeof(float) * E * h->nv));
-    const size_t pred_bytes = sizeof(int) * (size_t)E * (4 + (h->LA + h->LB <= 8 ? 24 : 32) / 2);
+    const int LTh = h->LA + h->LB;
+    const size_t pred_bytes = sizeof(int) * (size_t)E * (4 + (LTh <= 8 ? 24 : (LTh <= 12 ? 32 : 40)) / 2);      // Slab::MAXC
     CUDA_OK(cudaMalloc(&d.pred, pred_bytes)); CUDA_OK(cudaMemset(d.pred, 0, pred_bytes));
     CUDA_OK(cudaMalloc(&d.warm, sizeof(float) * E * h->nv)); CUDA_OK(cudaMalloc(&d.ep_ret, sizeof(float) * E));
     CUDA_OK(cudaMalloc(&d.ep_dret, sizeof(float) * E)); CUDA_OK(cudaMalloc(&d.ep_step, sizeof(int) * E));

@@ -45,6 +45,10 @@
 #define RS_SINCOS(x, s, c) sincosf((x), (s), (c))
 #define RS_DIV(a, b) ((a) / (b))
 #define RS_UNROLL1 _Pragma("unroll 1")
+#define RS_COLD __device__ __forceinline__
+#define RS_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define RS_LIKELY(x) __builtin_expect(!!(x), 1)
+#define RS_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #else
 #define RS_LANE_LOOP(i, n) for (int i = 0; i < (n); i++)
 #define RS_SYNC()
@@ -57,6 +61,10 @@
 #define RS_SINCOS(x, s, c) sincosf((x), (s), (c))
 #define RS_DIV(a, b) ((a) / (b))
 #define RS_UNROLL1
+#define RS_COLD static inline
+#define RS_WARP_ANY(p) (p)
+#define RS_LIKELY(x) (x)
+#define RS_UNLIKELY(x) (x)
 #endif
 
 
@@ -106,7 +114,7 @@ struct Slab {
     enum {
         LT = LA + LB, NQA = 7 + 2 * LA, NVA = 6 + 2 * LA, NVB = 6 + 2 * LB, NQ = 14 + 2 * LT, NV = 12 + 2 * LT, NU = 2 * LT,
         NVP = (NV | 1), NB = 2 + 2 * LT, NG = 2 + 3 * LT, NGA = 1 + 3 * LA, NGB = 1 + 3 * LB,
-        MAXC = (LT <= 8 ? 24 : 32),                       // contact capacity per pair
+        MAXC = (LT <= 8 ? 24 : (LT <= 12 ? 32 : 40)),     // contact capacity per pair (24 Ant pairs, 32 with a Bug, 40 with a Spider: its 3-sigma-action soak filled 32)
         // H storage: two per-agent blocks (row stride n+1) when the agents are uncoupled, one dense NV x NVP matrix when an
         // inter-agent contact couples them.  The dense form spills over the arrays that are dead between build_H and the
         // end of the linear solve (tw .. ljd below), so only HDED floats are dedicated to it.
@@ -481,6 +489,49 @@ RS_HD void sphere_vs_world(Ctx<LA, LB>& c, int body, V3 p, float r, float iw, V3
     }
 }
 
+// conservative filter for capsule_vs_box_edges: can the segment e0-e1 pass within R of one of the tatami's top or vertical edges?
+// (seen along a top edge, the segment's bounding rectangle grown by R must contain the edge; likewise from above for a vertical one)
+RS_HD bool near_box_edge(V3 e0, V3 e1, float R) {
+    const float top = RS_BOX_CZ + RS_BOX_HZ, bot = RS_BOX_CZ - RS_BOX_HZ;
+    const float xl = fminf(e0.x, e1.x) - R, xh = fmaxf(e0.x, e1.x) + R, yl = fminf(e0.y, e1.y) - R, yh = fmaxf(e0.y, e1.y) + R;
+    const float zl = fminf(e0.z, e1.z) - R, zh = fmaxf(e0.z, e1.z) + R;
+    const bool sx = (xl <= RS_BOX_HX && xh >= RS_BOX_HX) || (xl <= -RS_BOX_HX && xh >= -RS_BOX_HX);
+    const bool sy = (yl <= RS_BOX_HX && yh >= RS_BOX_HX) || (yl <= -RS_BOX_HX && yh >= -RS_BOX_HX);
+    return (zl <= top && zh >= top && (sx || sy)) || (sx && sy && zl <= top && zh >= bot);
+}
+
+// capsule INTERIOR (centre pc, unit axis ax, half length hl, radius r) against the tatami's four top and four vertical edges: the
+// closest edge whose nearest capsule point is interior to the segment and outside the box.  true = within the margin; *n points
+// from the box to the capsule, *be is the point on the edge.
+RS_COLD bool capsule_vs_box_edges(V3 pc, V3 ax, float hl, float r, float* dist, V3* be_out, V3* n_out) {
+    float best = 1e30f; V3 bg = pc, be = pc;
+    const float R = r + RS_MARGIN, top = RS_BOX_CZ + RS_BOX_HZ;
+    const float hx = hl * fabsf(ax.x) + R, hy = hl * fabsf(ax.y) + R, hz = hl * fabsf(ax.z) + R;      // half extents of the bounding box grown by R
+    RS_UNROLL1
+    for (int k = 0; k < 8; k++) {
+        // cheap reject, the same bound as near_box_edge for this one edge
+        if (k < 4) { const float sg = (k & 2) ? -RS_BOX_HX : RS_BOX_HX; if (fabsf(((k & 1) ? pc.x : pc.y) - sg) > ((k & 1) ? hx : hy) || fabsf(pc.z - top) > hz) continue; }
+        else if (fabsf(pc.x - ((k & 1) ? RS_BOX_HX : -RS_BOX_HX)) > hx || fabsf(pc.y - ((k & 2) ? RS_BOX_HX : -RS_BOX_HX)) > hy || fabsf(pc.z - RS_BOX_CZ) > hz + RS_BOX_HZ) continue;
+        // k < 4: top edges (y = +-HX along x, x = +-HX along y at z = top); k >= 4: the four vertical edges
+        V3 ep, ea; float el;
+        if (k < 4) { const float sg = (k & 2) ? -1.f : 1.f; ep = (k & 1) ? v3(sg * RS_BOX_HX, 0.f, RS_BOX_CZ + RS_BOX_HZ) : v3(0.f, sg * RS_BOX_HX, RS_BOX_CZ + RS_BOX_HZ);
+                     ea = (k & 1) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f); el = RS_BOX_HX; }
+        else { ep = v3((k & 1) ? RS_BOX_HX : -RS_BOX_HX, (k & 2) ? RS_BOX_HX : -RS_BOX_HX, RS_BOX_CZ); ea = v3(0.f, 0.f, 1.f); el = RS_BOX_HZ; }
+        if (fabsf(dot(ax, ea)) > 1.f - 1e-6f) continue;            // parallel: the endpoint tests cover it
+        V3 pg, pe;
+        seg_seg(pc, ax, hl, ep, ea, el, &pg, &pe);
+        if (fabsf(dot(pg - pc, ax)) >= hl * (1.f - 1e-6f)) continue;   // an endpoint is closest
+        if (fabsf(pg.x) < RS_BOX_HX && fabsf(pg.y) < RS_BOX_HX && fabsf(pg.z - RS_BOX_CZ) < RS_BOX_HZ) continue;   // inside: face push-out case
+        const float dd = norm(pg - pe) - r;
+        if (dd < best) { best = dd; bg = pg; be = pe; }
+    }
+    if (!(best < RS_MARGIN)) return false;
+    float l2;
+    *n_out = normalized(bg - be, &l2);
+    *be_out = be; *dist = best;
+    return l2 > 1e-12f;
+}
+
 template <int LA, int LB>
 RS_HD void collide(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
@@ -491,6 +542,7 @@ RS_HD void collide(Ctx<LA, LB>& c) {
     // loops below cull on it and only rebuild the geoms of the few pairs that pass
     static_assert(10 * S::NG <= S::HDED, "geom cache must fit in the H array");
     float* gc = s.H;
+    bool rim = false;
     // --- agent geoms against the world (floor plane, tatami box, four border rails) ---
     RS_LANE_LOOP(i, S::NG) {
         V3 e0, e1; float r, iw; int body, agent; bool sph;
@@ -502,42 +554,29 @@ RS_HD void collide(Ctx<LA, LB>& c) {
         // keys: geom i owns 12 slots: end0 {floor, box}, end1 {floor, box}, rails 4..7; pair contacts start at 12 * NG
         sphere_vs_world(c, body, e0, r, iw, ax, 12 * i, true);
         if (!sph) sphere_vs_world(c, body, e1, r, iw, ax, 12 * i + 2, true);
-        // capsule INTERIOR against the tatami's top and vertical edges (the distance from a segment to the box is attained at an
-        // endpoint -- the sphere tests above -- or on an edge): a leg straddling the edge at |x| = 2.3 rests on it instead of
-        // sinking through until an endpoint touches.  At most one contact (the closest edge), key slot 8.
-        if (!sph && (fmaxf(fabsf(e0.x), fabsf(e1.x)) + r + RS_MARGIN >= RS_BOX_HX || fmaxf(fabsf(e0.y), fabsf(e1.y)) + r + RS_MARGIN >= RS_BOX_HX)
-            && fminf(e0.z, e1.z) - r - RS_MARGIN < RS_BOX_CZ + RS_BOX_HZ) {
-            const V3 pc = 0.5f * (e0 + e1);
-            const float hl = 0.5f * len;
-            float best = 1e30f; V3 bg = pc, be = pc;
+        // the rim of the arena (border rails at +-2.0, tatami edges at +-2.3): flagged here, tested in the cold pass below
+        rim = rim || ((fmaxf(fmaxf(fabsf(e0.x), fabsf(e1.x)), fmaxf(fabsf(e0.y), fabsf(e1.y))) + r + RS_MARGIN + RS_RAIL_R >= RS_RAIL)
+                      && fminf(e0.z, e1.z) - r - RS_MARGIN - RS_RAIL_R < RS_RAIL_Z);
+    }
+    // Cold pass, entered only by pairs with a geom at the rim (they are about to be done, sumo.py:149-150), so that the hot
+    // instruction footprint of an evaluation does not carry it:
+    //  * border rails: thin cylinders treated as capsules of radius RS_RAIL_R, key slots 4..7;
+    //  * capsule INTERIOR against the tatami's top and vertical edges (the distance from a segment to the box is attained at an
+    //    endpoint -- the sphere tests above -- or on an edge): a leg straddling the edge at |x| = 2.3 rests on it instead of
+    //    sinking through until an endpoint touches.  At most one contact per capsule (the closest edge), key slot 8.
+    if (RS_UNLIKELY(RS_WARP_ANY(rim))) {
+        RS_LANE_LOOP(i, S::NG) {
+            V3 e0, e1; float r, iw; int body, agent; bool sph;
+            geom_of(c, i, &e0, &e1, &r, &body, &iw, &agent, &sph);
+            const float R = r + RS_MARGIN + RS_RAIL_R;
+            if (fmaxf(fmaxf(fabsf(e0.x), fabsf(e1.x)), fmaxf(fabsf(e0.y), fabsf(e1.y))) + R < RS_RAIL || fminf(e0.z, e1.z) - R >= RS_RAIL_Z) continue;
+            float len = 0.f;
+            const V3 ax = sph ? v3(0, 0, 0) : normalized(e1 - e0, &len);
             RS_UNROLL1
-            for (int k = 0; k < 8; k++) {
-                // k < 4: top edges (y = +-HX along x, x = +-HX along y at z = top); k >= 4: the four vertical edges
-                V3 ep, ea; float el;
-                if (k < 4) { const float sg = (k & 2) ? -1.f : 1.f; ep = (k & 1) ? v3(sg * RS_BOX_HX, 0.f, RS_BOX_CZ + RS_BOX_HZ) : v3(0.f, sg * RS_BOX_HX, RS_BOX_CZ + RS_BOX_HZ);
-                             ea = (k & 1) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f); el = RS_BOX_HX; }
-                else { ep = v3((k & 1) ? RS_BOX_HX : -RS_BOX_HX, (k & 2) ? RS_BOX_HX : -RS_BOX_HX, RS_BOX_CZ); ea = v3(0.f, 0.f, 1.f); el = RS_BOX_HZ; }
-                if (fabsf(dot(ax, ea)) > 1.f - 1e-6f) continue;            // parallel: the endpoint tests cover it
-                V3 pg, pe;
-                seg_seg(pc, ax, hl, ep, ea, el, &pg, &pe);
-                if (fabsf(dot(pg - pc, ax)) >= hl * (1.f - 1e-6f)) continue;   // an endpoint is closest
-                if (fabsf(pg.x) < RS_BOX_HX && fabsf(pg.y) < RS_BOX_HX && fabsf(pg.z - RS_BOX_CZ) < RS_BOX_HZ) continue;   // inside: face push-out case
-                const float dd = norm(pg - pe) - r;
-                if (dd < best) { best = dd; bg = pg; be = pe; }
-            }
-            if (best < RS_MARGIN) {
-                float l2;
-                const V3 n = normalized(bg - be, &l2);                    // from the box to the capsule
-                if (l2 > 1e-12f) add_contact(c, -1, body, best, be + (0.5f * best) * n, n, v3(0, 0, 0), iw, 12 * i + 8);
-            }
-        }
-        // rails (thin cylinders treated as capsules of radius RS_RAIL_R)
-        float mx = fmaxf(fabsf(e0.x), fabsf(e1.x)) + r + RS_MARGIN + RS_RAIL_R;
-        float my = fmaxf(fabsf(e0.y), fabsf(e1.y)) + r + RS_MARGIN + RS_RAIL_R;
-        float zlo = fminf(e0.z, e1.z) - r - RS_MARGIN - RS_RAIL_R;
-        if ((mx >= RS_RAIL || my >= RS_RAIL) && zlo < RS_RAIL_Z) {
             for (int k = 0; k < 4; k++) {
                 // top: y=+2 along x; right: x=+2 along y; bottom: y=-2 along x; left: x=-2 along y
+                const float reach = (k & 1) ? ((k & 2) ? -fminf(e0.x, e1.x) : fmaxf(e0.x, e1.x)) : ((k & 2) ? -fminf(e0.y, e1.y) : fmaxf(e0.y, e1.y));
+                if (reach + R < RS_RAIL) continue;      // this rail is out of reach
                 V3 rp = (k == 0) ? v3(0.f, RS_RAIL, RS_RAIL_Z) : (k == 1) ? v3(RS_RAIL, 0.f, RS_RAIL_Z) : (k == 2) ? v3(0.f, -RS_RAIL, RS_RAIL_Z) : v3(-RS_RAIL, 0.f, RS_RAIL_Z);
                 V3 ra = (k & 1) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
                 V3 pg, pr;
@@ -545,6 +584,9 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                 else seg_seg(0.5f * (e0 + e1), ax, 0.5f * len, rp, ra, RS_RAIL, &pg, &pr);
                 sph_sph(c, -1, body, pr, RS_RAIL_R, pg, r, iw, 12 * i + 4 + k);
             }
+            if (sph || !near_box_edge(e0, e1, r + RS_MARGIN)) continue;
+            V3 be, n; float best;
+            if (capsule_vs_box_edges(0.5f * (e0 + e1), ax, 0.5f * len, r, &best, &be, &n)) add_contact(c, -1, body, best, be + (0.5f * best) * n, n, v3(0, 0, 0), iw, 12 * i + 8);
         }
     }
     RS_SYNC();
@@ -1340,9 +1382,9 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
     RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
     RS_SYNC();
     RS_ACC(0);
-    if (RS_ARROW && s.coupled == 0) build_H_arrow(c); else build_H(c);
+    if (RS_LIKELY(RS_ARROW && s.coupled == 0)) build_H_arrow(c); else build_H(c);
     RS_ACC(1);
-    if (RS_ARROW && s.coupled == 0) arrow_solve(c); else chol_solve(c);      // s.d = -H^-1 grad
+    if (RS_LIKELY(RS_ARROW && s.coupled == 0)) arrow_solve(c); else chol_solve(c);      // s.d = -H^-1 grad
     RS_ACC(2);
     twists(c, s.d);
     rows_of(c, s.d, s.cjd, s.ljd);
@@ -1375,7 +1417,7 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
         mat_vec(c, s.d, s.Md, (const float*)0);
     }
     float alpha = 1.f;
-    if (!same && !predicted) alpha = line_search(c);
+    if (RS_UNLIKELY(!same && !predicted)) alpha = line_search(c);
 #ifdef RS_LS_DEBUG
     printf(" iter: same %d predicted %d alpha %g ncon %d coupled %d\n", same, predicted, alpha, s.ncon, s.coupled);
 #endif
