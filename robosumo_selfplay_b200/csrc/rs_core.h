@@ -144,7 +144,7 @@ struct Slab {
     float ljd[NU];
     // ---- contacts: position, normal, first tangent (second = n x t1), D, rows ----
     float cpos[MAXC][3], cn[MAXC][3], ct1[MAXC][3], cD[MAXC];
-    float caref[MAXC][4], cjar[MAXC][4];          // (dynamics() borrows these two as leg-inertia scratch)
+    float caref[MAXC][4], cjar[MAXC][4];          // (dynamics() borrows these two as link-inertia scratch)
     int cbody[MAXC];                               // (bA + 1) | (bB + 1) << 8 | key << 16 | active rows << 28 ; body -1 = world
     unsigned short cprev[MAXC];                    // contacts of the previous evaluation: key << 4 | final active rows
     int nprev;
@@ -155,7 +155,6 @@ struct Slab {
     int coupled;                              // bit 0: an inter-agent contact couples the two agents, bit 1: an intra-agent (leg-leg) contact; 0: H keeps M's arrowhead form
     int lmask, pmask, pvalid;                 // limit rows: active set in use / predicted from the previous evaluation / prediction valid
     int tot_iter, tot_coupled, tot_ncon, max_iter;      // diagnostics accumulated over one env step
-    RS_HD float* legI(int g) { return &caref[0][0] + 10 * g; }
     RS_HD int bA(int k) const { return (cbody[k] & 255) - 1; }
     RS_HD int bB(int k) const { return ((cbody[k] >> 8) & 255) - 1; }
     RS_HD int ckey(int k) const { return (cbody[k] >> 16) & 4095; }
@@ -167,7 +166,6 @@ struct Slab {
         return ir >= NVA ? BSA + (ir - NVA) * (NVB + 1) + (ic - NVA) : ir * (NVA + 1) + ic;
     }
 };
-static_assert(2 * RS_MAXL * 10 <= 2 * 32 * 4, "leg inertia scratch must fit in caref + cjar");
 
 template <int LA, int LB>
 struct Ctx {
@@ -271,59 +269,91 @@ template <int LA, int LB>
 RS_HD void dynamics(Ctx<LA, LB>& c) {
     typedef Slab<LA, LB> S;
     S& s = *c.s;
-    RS_LANE_LOOP(g, S::LT) {
-        int a = c.agent_of_leg(g), l = g - c.leg0(a);
+    // Lane-parallel formulation: the per-leg work is cut into three equal-shaped items (the same instruction stream on different
+    // data, so a warp runs 3 * LT lanes instead of LT): j = 0 the ankle link with the ankle motion s_a, j = 1 the hip link with the
+    // hip motion s_h, j = 2 the ankle link with s_h (the cross term of the hip column).  Items 0 / 1 also carry their link's
+    // spatial inertia about O and its RNE force.  Results are parked in scratch that is dead during dynamics (the alias zone and
+    // caref | cjar) and combined by a second pass (lane = joint) and a summation pass (lane = agent x component).
+    float* X = &s.tw[0][0];                 // [LT][3][6]  I * s      (n about O, f)
+    float* F = X + 18 * S::LT;              // [LT][2][6]  RNE force of the link (n about O, f): [0] ankle link, [1] hip link
+    float* LI = &s.caref[0][0];             // [LT][2][10] spatial inertia of the link about O
+    static_assert(30 * S::LT <= S::ALIAS, "dynamics scratch must fit in the alias zone");
+    static_assert(20 * S::LT <= 8 * S::MAXC, "link inertia scratch must fit in caref + cjar");
+    RS_LANE_LOOP(i, 3 * S::LT) {
+        const int g = i / 3, j = i - 3 * g;
+        const int a = c.agent_of_leg(g), l = g - c.leg0(a);
         const rs_agent_model& m = c.am[a];
         const float* R = s.Rt[a];
-        int va = c.vadr(a), dh = c.hipdof(g), da = dh + 1;
-        V3 O = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]) - O, pa = ld3(s.org[c.bank(g)]) - O, pt = ld3(s.tip[g]) - O;
-        V3 axh = c.hip_axis(g), axa = ld3(s.axa[g]);
+        const V3 O = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]) - O, pa = ld3(s.org[c.bank(g)]) - O, pt = ld3(s.tip[g]) - O;
+        const V3 axh = c.hip_axis(g), axa = ld3(s.axa[g]);
+        const bool hipl = (j == 1);          // this item's link
         float len;
-        Cap hip, ank;
-        hip.m = m.m_hip[l]; hip.ip = m.ip_hip[l]; hip.ia = m.ia_hip[l]; hip.c = 0.5f * (ph + pa); hip.u = normalized(pa - ph, &len);
-        ank.m = m.m_ank[l]; ank.ip = m.ip_ank[l]; ank.ia = m.ia_ank[l]; ank.c = 0.5f * (pa + pt); ank.u = normalized(pt - pa, &len);
+        Cap b;
+        b.m = hipl ? m.m_hip[l] : m.m_ank[l]; b.ip = hipl ? m.ip_hip[l] : m.ip_ank[l]; b.ia = hipl ? m.ia_hip[l] : m.ia_ank[l];
+        const V3 p0 = hipl ? ph : pa, p1 = hipl ? pa : pt;
+        b.c = 0.5f * (p0 + p1); b.u = normalized(p1 - p0, &len);
         // motion subspaces about O: rotation about axis through point p  ->  (axis, axis x (O - p)) = (axis, -axis x p)
-        V3 sa_v = cross(pa, axa), sh_v = cross(ph, axh);
-        V3 nA, fA, nH, fH, n2, f2;
-        applyI(ank, axa, sa_v, &nA, &fA);                       // I_ank s_a
-        applyI(hip, axh, sh_v, &nH, &fH);                       // (I_hip + I_ank) s_h
-        applyI(ank, axh, sh_v, &n2, &f2);
-        nH = nH + n2; fH = fH + f2;
-        float Maa = dot(axa, nA) + dot(sa_v, fA) + m.armature;
-        float Mha = dot(axh, nA) + dot(sh_v, fA);
-        float Mhh = dot(axh, nH) + dot(sh_v, fH) + m.armature;
-        s.Ml[g][0] = Mhh; s.Ml[g][1] = Mha; s.Ml[g][2] = Maa;
-        V3 rA = mulRT(R, nA), rH = mulRT(R, nH);
-        float colA[6] = { fA.x, fA.y, fA.z, rA.x, rA.y, rA.z }, colH[6] = { fH.x, fH.y, fH.z, rH.x, rH.y, rH.z };
-        for (int k = 0; k < 6; k++) { s.Mc[g][2 * k] = colH[k]; s.Mc[g][2 * k + 1] = colA[k]; }
-        float I10[10];
-        for (int k = 0; k < 10; k++) I10[k] = 0.f;
-        accI(hip, I10); accI(ank, I10);
-        for (int k = 0; k < 10; k++) s.legI(g)[k] = I10[k];
-        // ---- RNE with qacc = 0 ----
-        const float* vv = s.v + va;
-        V3 wt = mulR(R, v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
-        V3 at_lin = cross(vt, wt);  at_lin.z += RS_GRAV;        // spatial accel of torso: (0, -w x v - g)
-        float qdh = s.v[dh], qda = s.v[da];
-        // hip body: v = v_t + s_h qd ; a = a_t + (v_t x s_h) qd
-        V3 wh = wt + qdh * axh, vh = vt + qdh * sh_v;
-        V3 alh = qdh * cross(wt, axh);
-        V3 ah = at_lin + qdh * (cross(wt, sh_v) + cross(vt, axh));
-        // ankle body: a = a_h + (v_h x s_a) qd
-        V3 wa = wh + qda * axa, vaO = vh + qda * sa_v;
-        V3 ala = alh + qda * cross(wh, axa);
-        V3 aa = ah + qda * (cross(wh, sa_v) + cross(vh, axa));
-        V3 nFa, fFa, nFh, fFh;
-        bodyForce(ank, wa, vaO, ala, aa, &nFa, &fFa);
-        bodyForce(hip, wh, vh, alh, ah, &nFh, &fFh);
-        nFh = nFh + nFa; fFh = fFh + fFa;                       // hip subtree
-        float bias_a = dot(axa, nFa) + dot(sa_v, fFa);
-        float bias_h = dot(axh, nFh) + dot(sh_v, fFh);
-        int ua = (a ? 2 * LA : 0) + 2 * l;
-        s.r[dh] = m.damping * qdh - s.act[ua] + bias_h;            // -qfrc_smooth
-        s.r[da] = m.damping * qda - s.act[ua + 1] + bias_a;
-        s.legF[g][0] = nFh.x; s.legF[g][1] = nFh.y; s.legF[g][2] = nFh.z;
-        s.legF[g][3] = fFh.x; s.legF[g][4] = fFh.y; s.legF[g][5] = fFh.z;
+        const V3 sa_v = cross(pa, axa), sh_v = cross(ph, axh);
+        V3 n, f;
+        applyI(b, j == 0 ? axa : axh, j == 0 ? sa_v : sh_v, &n, &f);
+        st3(X + 18 * g + 6 * j, n); st3(X + 18 * g + 6 * j + 3, f);
+        if (j < 2) {
+            float I10[10];
+            for (int k = 0; k < 10; k++) I10[k] = 0.f;
+            accI(b, I10);
+            for (int k = 0; k < 10; k++) LI[20 * g + 10 * j + k] = I10[k];
+            // ---- RNE with qacc = 0 ----
+            const float* vv = s.v + c.vadr(a);
+            const int dh = c.hipdof(g);
+            const V3 wt = mulR(R, v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
+            V3 at_lin = cross(vt, wt);  at_lin.z += RS_GRAV;        // spatial accel of torso: (0, -w x v - g)
+            const float qdh = s.v[dh], qda = hipl ? 0.f : s.v[dh + 1];
+            // hip body: v = v_t + s_h qd ; a = a_t + (v_t x s_h) qd
+            const V3 wh = wt + qdh * axh, vh = vt + qdh * sh_v;
+            const V3 alh = qdh * cross(wt, axh);
+            const V3 ah = at_lin + qdh * (cross(wt, sh_v) + cross(vt, axh));
+            // ankle body: a = a_h + (v_h x s_a) qd   (qda = 0 for the hip item: the same expressions return the hip body's motion)
+            const V3 wa = wh + qda * axa, vaO = vh + qda * sa_v;
+            const V3 ala = alh + qda * cross(wh, axa);
+            const V3 aa = ah + qda * (cross(wh, sa_v) + cross(vh, axa));
+            V3 nF, fF;
+            bodyForce(b, wa, vaO, ala, aa, &nF, &fF);
+            st3(F + 12 * g + 6 * j, nF); st3(F + 12 * g + 6 * j + 3, fF);
+        }
+    }
+    RS_SYNC();
+    // lane = joint (leg g, col 0 = hip, 1 = ankle): the joint's column of M and its bias force
+    RS_LANE_LOOP(i, 2 * S::LT) {
+        const int g = i >> 1, col = i & 1;
+        const int a = c.agent_of_leg(g), l = g - c.leg0(a);
+        const rs_agent_model& m = c.am[a];
+        const float* R = s.Rt[a];
+        const V3 O = ld3(s.org[a]), ph = ld3(s.org[c.bhip(g)]) - O, pa = ld3(s.org[c.bank(g)]) - O;
+        const V3 axh = c.hip_axis(g), axa = ld3(s.axa[g]);
+        const V3 sa_v = cross(pa, axa), sh_v = cross(ph, axh);
+        const float* x = X + 18 * g; const float* fo = F + 12 * g;
+        // column: ankle = I_ank s_a ; hip = (I_hip + I_ank) s_h.  bias: ankle = its link's force ; hip = the leg subtree's
+        V3 n = ld3(x + (col ? 0 : 6)), f = ld3(x + (col ? 3 : 9)), nF = ld3(fo), fF = ld3(fo + 3);
+        if (!col) { n = n + ld3(x + 12); f = f + ld3(x + 15); nF = nF + ld3(fo + 6); fF = fF + ld3(fo + 9); }
+        const V3 ax = col ? axa : axh, sv = col ? sa_v : sh_v;
+        s.Ml[g][2 * col] = dot(ax, n) + dot(sv, f) + m.armature;                 // Mhh / Maa
+        if (col) s.Ml[g][1] = dot(axh, n) + dot(sh_v, f);                        // Mha
+        const V3 rr = mulRT(R, n);
+        const float colv[6] = { f.x, f.y, f.z, rr.x, rr.y, rr.z };
+        for (int k = 0; k < 6; k++) s.Mc[g][2 * k + col] = colv[k];
+        const int dof = c.hipdof(g) + col, ua = (a ? 2 * LA : 0) + 2 * l + col;
+        s.r[dof] = m.damping * s.v[dof] - s.act[ua] + dot(ax, nF) + dot(sv, fF);      // -qfrc_smooth
+    }
+    // lane = agent x component: sums over the agent's legs of the link inertias (10) and the subtree forces (6) -> s.scr[a][16]
+    RS_LANE_LOOP(i, 32) {
+        const int a = i >> 4, k = i & 15;
+        float acc = 0.f;
+        RS_UNROLL1
+        for (int l = 0; l < c.L(a); l++) {
+            const int g = c.leg0(a) + l;
+            acc += k < 10 ? LI[20 * g + k] + LI[20 * g + 10 + k] : F[12 * g + (k - 10)] + F[12 * g + 6 + (k - 10)];
+        }
+        s.scr[i] = acc;
     }
     RS_SYNC();
     RS_LANE_LOOP(a, 2) {
@@ -343,12 +373,8 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         I10[0] = m.mT; I10[1] = m.mT * cT.x; I10[2] = m.mT * cT.y; I10[3] = m.mT * cT.z;
         I10[4] = IT[0] + m.mT * (cc - cT.x * cT.x); I10[5] = IT[1] - m.mT * cT.x * cT.y; I10[6] = IT[2] - m.mT * cT.x * cT.z;
         I10[7] = IT[4] + m.mT * (cc - cT.y * cT.y); I10[8] = IT[5] - m.mT * cT.y * cT.z; I10[9] = IT[8] + m.mT * (cc - cT.z * cT.z);
-        V3 nsum = v3(0, 0, 0), fsum = v3(0, 0, 0);
-        for (int l = 0; l < c.L(a); l++) {
-            int g = c.leg0(a) + l;
-            for (int k = 0; k < 10; k++) I10[k] += s.legI(g)[k];
-            nsum = nsum + ld3(s.legF[g]); fsum = fsum + ld3(s.legF[g] + 3);
-        }
+        for (int k = 0; k < 10; k++) I10[k] += s.scr[16 * a + k];
+        const V3 nsum = ld3(s.scr + 16 * a + 10), fsum = ld3(s.scr + 16 * a + 13);
         float mt = I10[0];
         V3 mc = v3(I10[1], I10[2], I10[3]);
         // root block: lin-lin m I ; lin-ang: column k = (R e_k) x mc ; ang-ang: R^T I_O R
@@ -1023,38 +1049,56 @@ RS_HD void build_H_arrow(Ctx<LA, LB>& c) {
     RS_LANE_LOOP(i, (int)AR::NCOPY) { H[i] = (&s.Mr[0][0])[i]; }
     RS_SYNC();
     RS_LANE_LOOP(j, S::NU) { if ((s.lmask >> j) & 1) H[AR::D0 + 3 * (j >> 1) + 2 * (j & 1)] += s.lD[j]; }
-    RS_SYNC();
     const int ncon = s.ncon;
-    for (int k = 0; k < ncon; k++) {
-        const int act = s.cact(k);
-        float a0 = (float)(act & 1), a1 = (float)((act >> 1) & 1), a2 = (float)((act >> 2) & 1), a3 = (float)((act >> 3) & 1);
-        float na = a0 + a1 + a2 + a3;
-        if (na == 0.f) continue;       // uniform across the warp (shared data)
-        float D = s.cD[k];
-        float cnn = D * na, cn1 = RS_MU * D * (a0 - a1), c11 = RS_MU * RS_MU * D * (a0 + a1);
-        float cn2 = RS_MU * D * (a2 - a3), c22 = RS_MU * RS_MU * D * (a2 + a3);
-        float* sc = s.scr;
-        const int b = s.bB(k) >= 0 ? s.bB(k) : s.bA(k);      // the other side is the world
-        RS_LANE_LOOP(e, 8) {
-            V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
+    // The cost of this routine per contact is what makes a block wait for its slowest warp (the warps re-align per Newton
+    // iteration), so the contacts are handled side by side: one pass computes the direction Jacobians of ALL contacts (lane =
+    // contact x chain dof: J(dir) = jc . dir for the 8 dofs of the touched body's chain, zero where the chain has no such dof),
+    // parked in the alias zone (dead between the gradient and the end of the linear solve); then one 32-lane pass per ACTIVE
+    // contact adds its 8 x 8 block  J^T D J  (lane = row r x column pair) into A | B | Dg.
+    enum { CHUNK = S::ALIAS / 24 < 16 ? S::ALIAS / 24 : 16 };
+    float* SC = &s.tw[0][0];
+    RS_UNROLL1
+    for (int k0 = 0; k0 < ncon; k0 += CHUNK) {
+        const int nk = ncon - k0 < CHUNK ? ncon - k0 : (int)CHUNK;
+        RS_LANE_LOOP(i, 8 * nk) {
+            const int k = k0 + (i >> 3), e = i & 7;
+            const int b = s.bB(k) >= 0 ? s.bB(k) : s.bA(k);      // the other side is the world
+            const V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
             int idx;
             const V3 jc = side_col(c, b, e, p, false, &idx);
-            sc[e] = (float)idx; sc[16 + e] = dot(jc, n); sc[32 + e] = dot(jc, t1); sc[48 + e] = dot(jc, cross(n, t1));
+            float* o = SC + 3 * i;
+            o[0] = dot(jc, n); o[1] = dot(jc, t1); o[2] = dot(jc, cross(n, t1));      // (jc = 0 where idx < 0)
         }
         RS_SYNC();
-        const int g = b < 2 ? -1 : (b - 2) % S::LT, a = b < 2 ? b : c.agent_of_leg(g);
-        RS_LANE_LOOP(e, 64) {
-            const int r = e >> 3, cc = e & 7;
-            if (r <= cc && sc[r] >= 0.f && sc[cc] >= 0.f) {
-                float nr = sc[16 + r], nc = sc[16 + cc], t1r = sc[32 + r], t1c = sc[32 + cc], t2r = sc[48 + r], t2c = sc[48 + cc];
-                float val = cnn * nr * nc + cn1 * (nr * t1c + t1r * nc) + c11 * t1r * t1c + cn2 * (nr * t2c + t2r * nc) + c22 * t2r * t2c;
-                if (cc < 6) { H[AR::A0 + a * 36 + r * 6 + cc] += val; if (r != cc) H[AR::A0 + a * 36 + cc * 6 + r] += val; }
-                else if (r < 6) H[AR::B0 + 12 * g + 2 * r + (cc - 6)] += val;
-                else H[AR::D0 + 3 * g + (r - 6) + (cc - 6)] += val;
+        RS_UNROLL1
+        for (int k = k0; k < k0 + nk; k++) {
+            const int act = s.cact(k);
+            if (act == 0) continue;        // uniform across the warp (shared data)
+            const float a0 = (float)(act & 1), a1 = (float)((act >> 1) & 1), a2 = (float)((act >> 2) & 1), a3 = (float)((act >> 3) & 1);
+            const float D = s.cD[k];
+            const float cnn = D * (a0 + a1 + a2 + a3), cn1 = RS_MU * D * (a0 - a1), c11 = RS_MU * RS_MU * D * (a0 + a1);
+            const float cn2 = RS_MU * D * (a2 - a3), c22 = RS_MU * RS_MU * D * (a2 + a3);
+            const int b = s.bB(k) >= 0 ? s.bB(k) : s.bA(k);
+            const int g = b < 2 ? 0 : (b - 2) % S::LT, a = b < 2 ? b : c.agent_of_leg(g);
+            const int ndof = b < 2 ? 6 : (b < 2 + S::LT ? 7 : 8);                     // dofs of the chain: root, + hip, + ankle
+            const float* sc = SC + 24 * (k - k0);
+            RS_LANE_LOOP(e, 32) {
+                const int r = e >> 2, c0 = (e & 3) << 1;
+                if (r < ndof && c0 < ndof) {
+                    const float nr = sc[3 * r], t1r = sc[3 * r + 1], t2r = sc[3 * r + 2];
+                    for (int cc = c0; cc < c0 + 2; cc++) {
+                        if (cc >= ndof || (r >= 6 && cc < r)) continue;      // the leg rows only hold their own 2 x 2 upper triangle
+                        const float nc = sc[3 * cc], t1c = sc[3 * cc + 1], t2c = sc[3 * cc + 2];
+                        const float val = nr * (cnn * nc + cn1 * t1c + cn2 * t2c) + t1r * (cn1 * nc + c11 * t1c) + t2r * (cn2 * nc + c22 * t2c);
+                        if (r < 6) { if (cc < 6) H[AR::A0 + a * 36 + r * 6 + cc] += val; else H[AR::B0 + 12 * g + 2 * r + (cc - 6)] += val; }
+                        else H[AR::D0 + 3 * g + (r - 6) + (cc - 6)] += val;
+                    }
+                }
             }
+            RS_SYNC();
         }
-        RS_SYNC();
     }
+    RS_SYNC();
 }
 
 // s.d = -H^-1 s.d for the compact arrowhead H of build_H_arrow
