@@ -155,6 +155,7 @@ struct Slab {
     int coupled;                              // bit 0: an inter-agent contact couples the two agents, bit 1: an intra-agent (leg-leg) contact; 0: H keeps M's arrowhead form
     int lmask, pmask, pvalid;                 // limit rows: active set in use / predicted from the previous evaluation / prediction valid
     int tot_iter, tot_coupled, tot_ncon, max_iter;      // diagnostics accumulated over one env step
+    int wood_m, wood_k[2];                    // inter-agent contacts with active rows in this iteration (count, first two indices)
     RS_HD int bA(int k) const { return (cbody[k] & 255) - 1; }
     RS_HD int bB(int k) const { return ((cbody[k] >> 8) & 255) - 1; }
     RS_HD int ckey(int k) const { return (cbody[k] >> 16) & 4095; }
@@ -356,57 +357,46 @@ RS_HD void dynamics(Ctx<LA, LB>& c) {
         s.scr[i] = acc;
     }
     RS_SYNC();
-    RS_LANE_LOOP(a, 2) {
+    // root blocks and root bias, lane = agent x body axis k: column k of the lin-ang and ang-ang blocks (the torso group is rigid, so
+    // its own part of the ang-ang block is the constant body-frame inertia about the torso origin; only the legs' part is rotated),
+    // then the torso group's RNE (computed by the three lanes of an agent alike, stored by the first)
+    RS_LANE_LOOP(i, 6) {
+        const int a = i >= 3 ? 1 : 0, k = i - 3 * a;
         const rs_agent_model& m = c.am[a];
         const float* R = s.Rt[a];
-        int va = c.vadr(a);
-        // torso group in world axes about the torso origin
-        V3 cT = mulR(R, ld3(m.cT));
-        float IT[9];   // R IT R^T
-        {   // R IT R^T, IT symmetric: T = IT R^T (columns = IT applied to rows of R), then R T
-            V3 t0 = mulR(m.IT, v3(R[0], R[1], R[2])), t1 = mulR(m.IT, v3(R[3], R[4], R[5])), t2 = mulR(m.IT, v3(R[6], R[7], R[8]));
-            V3 c0 = mulR(R, t0), c1 = mulR(R, t1), c2 = mulR(R, t2);
-            IT[0] = c0.x; IT[3] = c0.y; IT[6] = c0.z; IT[1] = c1.x; IT[4] = c1.y; IT[7] = c1.z; IT[2] = c2.x; IT[5] = c2.y; IT[8] = c2.z;
-        }
-        float I10[10];
-        float cc = dot(cT, cT);
-        I10[0] = m.mT; I10[1] = m.mT * cT.x; I10[2] = m.mT * cT.y; I10[3] = m.mT * cT.z;
-        I10[4] = IT[0] + m.mT * (cc - cT.x * cT.x); I10[5] = IT[1] - m.mT * cT.x * cT.y; I10[6] = IT[2] - m.mT * cT.x * cT.z;
-        I10[7] = IT[4] + m.mT * (cc - cT.y * cT.y); I10[8] = IT[5] - m.mT * cT.y * cT.z; I10[9] = IT[8] + m.mT * (cc - cT.z * cT.z);
-        for (int k = 0; k < 10; k++) I10[k] += s.scr[16 * a + k];
-        const V3 nsum = ld3(s.scr + 16 * a + 10), fsum = ld3(s.scr + 16 * a + 13);
-        float mt = I10[0];
-        V3 mc = v3(I10[1], I10[2], I10[3]);
-        // root block: lin-lin m I ; lin-ang: column k = (R e_k) x mc ; ang-ang: R^T I_O R
+        const int va = c.vadr(a);
+        const float* sum = s.scr + 16 * a;                       // legs: m, m c (3), I about O (6), subtree torque (3), force (3)
+        const V3 cL = ld3(m.cT), cT = mulR(R, cL);               // torso-group com, body / world axes
+        const float mt = m.mT + sum[0];
+        const V3 mc = m.mT * cT + ld3(sum + 1);
         float* Mr = s.Mr[a];
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Mr[i * 6 + j] = (i == j) ? mt : 0.f;
-        float IO[9] = { I10[4], I10[5], I10[6], I10[5], I10[7], I10[8], I10[6], I10[8], I10[9] };
-        for (int k = 0; k < 3; k++) {
-            V3 ek = v3(R[k], R[3 + k], R[6 + k]);
-            V3 f = cross(ek, mc);
-            V3 n = mulR(IO, ek);
-            V3 nb = mulRT(R, n);
-            Mr[0 * 6 + 3 + k] = f.x; Mr[(3 + k) * 6 + 0] = f.x;
-            Mr[1 * 6 + 3 + k] = f.y; Mr[(3 + k) * 6 + 1] = f.y;
-            Mr[2 * 6 + 3 + k] = f.z; Mr[(3 + k) * 6 + 2] = f.z;
-            Mr[3 * 6 + 3 + k] = nb.x; Mr[4 * 6 + 3 + k] = nb.y; Mr[5 * 6 + 3 + k] = nb.z;
-        }
-        // torso group RNE
+        for (int j = 0; j < 3; j++) Mr[k * 6 + j] = (j == k) ? mt : 0.f;
+        const V3 ek = v3(R[k], R[3 + k], R[6 + k]);
+        const V3 f = cross(ek, mc);
+        const V3 nl = v3(sum[4] * ek.x + sum[5] * ek.y + sum[6] * ek.z, sum[5] * ek.x + sum[7] * ek.y + sum[8] * ek.z, sum[6] * ek.x + sum[8] * ek.y + sum[9] * ek.z);
+        const float ck = k == 0 ? cL.x : (k == 1 ? cL.y : cL.z), cc = dot(cL, cL);
+        V3 nb = v3(m.IT[k], m.IT[3 + k], m.IT[6 + k]) + m.mT * (v3(k == 0 ? cc : 0.f, k == 1 ? cc : 0.f, k == 2 ? cc : 0.f) - ck * cL) + mulRT(R, nl);
+        Mr[0 * 6 + 3 + k] = f.x; Mr[(3 + k) * 6 + 0] = f.x;
+        Mr[1 * 6 + 3 + k] = f.y; Mr[(3 + k) * 6 + 1] = f.y;
+        Mr[2 * 6 + 3 + k] = f.z; Mr[(3 + k) * 6 + 2] = f.z;
+        Mr[3 * 6 + 3 + k] = nb.x; Mr[4 * 6 + 3 + k] = nb.y; Mr[5 * 6 + 3 + k] = nb.z;
+        // torso group RNE (generic full-inertia body force; I_world w = R (IT w_body))
         const float* vv = s.v + va;
-        V3 wt = mulR(R, v3(vv[3], vv[4], vv[5])), vt = v3(vv[0], vv[1], vv[2]);
+        const V3 wb = v3(vv[3], vv[4], vv[5]);
+        const V3 wt = mulR(R, wb), vt = v3(vv[0], vv[1], vv[2]);
         V3 at_lin = cross(vt, wt);  at_lin.z += RS_GRAV;
-        // generic (full inertia) body force for the torso group
-        V3 vc = vt + cross(wt, cT);
-        V3 hf = m.mT * vc;
-        V3 hn = mulR(IT, wt) + cross(cT, hf);
-        V3 af = m.mT * at_lin;               // alpha = 0
-        V3 an = cross(cT, af);
-        V3 nT = an + cross(wt, hn) + cross(vt, hf);
-        V3 fT = af + cross(wt, hf);
-        nT = nT + nsum; fT = fT + fsum;
-        V3 nb = mulRT(R, nT);
-        s.r[va + 0] = fT.x; s.r[va + 1] = fT.y; s.r[va + 2] = fT.z;            // -qfrc_smooth (root: bias only)
-        s.r[va + 3] = nb.x; s.r[va + 4] = nb.y; s.r[va + 5] = nb.z;
+        const V3 vc = vt + cross(wt, cT);
+        const V3 hf = m.mT * vc;
+        const V3 hn = mulR(R, mulR(m.IT, wb)) + cross(cT, hf);
+        const V3 af = m.mT * at_lin;               // alpha = 0
+        const V3 an = cross(cT, af);
+        const V3 nT = an + cross(wt, hn) + cross(vt, hf) + ld3(sum + 10);
+        const V3 fT = af + cross(wt, hf) + ld3(sum + 13);
+        const V3 nbT = mulRT(R, nT);
+        if (k == 0) {
+            s.r[va + 0] = fT.x; s.r[va + 1] = fT.y; s.r[va + 2] = fT.z;            // -qfrc_smooth (root: bias only)
+            s.r[va + 3] = nbT.x; s.r[va + 4] = nbT.y; s.r[va + 5] = nbT.z;
+        }
     }
     RS_SYNC();
 }
@@ -621,6 +611,9 @@ RS_HD void collide(Ctx<LA, LB>& c) {
         V3 dt = ld3(s.org[1]) - ld3(s.org[0]);
         // (a tighter bound from the actual geom extents was measured: it skips the pair loop more often but does not pay for its atomics)
         float reach = c.am[0].reach + c.am[1].reach + RS_MARGIN;
+#ifdef RS_EXPERIMENT_NO_PAIRS
+        reach = 0.f;      // developer experiment: what would the step cost without inter-agent contacts?
+#endif
         if (dot(dt, dt) < reach * reach) {
             RS_LANE_LOOP(p, S::NGA * S::NGB) {
                 int ia = p / S::NGB, ib = p - ia * S::NGB;
@@ -639,6 +632,9 @@ RS_HD void collide(Ctx<LA, LB>& c) {
                     else if (sA) { pA = a0; pB = seg_nearest(b0, b1, a0); }
                     else if (sB) { pB = b0; pA = seg_nearest(a0, a1, b0); }
                     else seg_seg(ca, ld3(GA + 3), GA[6], cb, ld3(GB + 3), GB[6], &pA, &pB);
+#ifdef RS_EXPERIMENT_NO_PAIR_CONTACTS
+                    if (c.max_newton < 0)      // developer experiment: run the pair tests, drop their contacts
+#endif
                     sph_sph(c, bA, bB, pA, rA, pB, rB, iwA + iwB, 12 * S::NG + p);
                 }
             }
@@ -1062,7 +1058,8 @@ RS_HD void build_H_arrow(Ctx<LA, LB>& c) {
         const int nk = ncon - k0 < CHUNK ? ncon - k0 : (int)CHUNK;
         RS_LANE_LOOP(i, 8 * nk) {
             const int k = k0 + (i >> 3), e = i & 7;
-            const int b = s.bB(k) >= 0 ? s.bB(k) : s.bA(k);      // the other side is the world
+            if (s.bA(k) >= 0) continue;                           // inter-agent contact: low-rank correction, woodbury_solve()
+            const int b = s.bB(k);                                // the other side is the world
             const V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
             int idx;
             const V3 jc = side_col(c, b, e, p, false, &idx);
@@ -1073,12 +1070,12 @@ RS_HD void build_H_arrow(Ctx<LA, LB>& c) {
         RS_UNROLL1
         for (int k = k0; k < k0 + nk; k++) {
             const int act = s.cact(k);
-            if (act == 0) continue;        // uniform across the warp (shared data)
+            if (act == 0 || s.bA(k) >= 0) continue;        // uniform across the warp (shared data)
             const float a0 = (float)(act & 1), a1 = (float)((act >> 1) & 1), a2 = (float)((act >> 2) & 1), a3 = (float)((act >> 3) & 1);
             const float D = s.cD[k];
             const float cnn = D * (a0 + a1 + a2 + a3), cn1 = RS_MU * D * (a0 - a1), c11 = RS_MU * RS_MU * D * (a0 + a1);
             const float cn2 = RS_MU * D * (a2 - a3), c22 = RS_MU * RS_MU * D * (a2 + a3);
-            const int b = s.bB(k) >= 0 ? s.bB(k) : s.bA(k);
+            const int b = s.bB(k);
             const int g = b < 2 ? 0 : (b - 2) % S::LT, a = b < 2 ? b : c.agent_of_leg(g);
             const int ndof = b < 2 ? 6 : (b < 2 + S::LT ? 7 : 8);                     // dofs of the chain: root, + hip, + ankle
             const float* sc = SC + 24 * (k - k0);
@@ -1210,6 +1207,209 @@ RS_HD void arrow_solve(Ctx<LA, LB>& c) {
         float dh_ = H[AR::Y0 + 2 * g], da_ = H[AR::Y0 + 2 * g + 1];
         for (int k = 0; k < 6; k++) { const float dt = s.d[c.vadr(a) + k]; dh_ -= W[2 * k] * dt; da_ -= W[2 * k + 1] * dt; }
         s.d[dh] = dh_; s.d[dh + 1] = da_;
+    }
+    RS_SYNC();
+}
+
+// ---- inter-agent contacts as a low-rank correction of the arrowhead solve -------------------------------------------------
+// A contact between the two agents couples them: H = H0 + U^T W U with H0 the arrowhead matrix of everything else, U the three
+// direction Jacobians (n, t1, t2; 28-vectors with the 8 chain dofs of each touched body) of the m such contacts with active rows
+// and W the 3 x 3 weights of their active pyramid rows.  The dense 28 x 29 elimination this used to take made the pair the
+// straggler of its block in every iteration (and streamed 4.5 k instructions through the instruction cache for one warp).  Here:
+//   X = H0^-1 [ -g | U^T ]   one arrowhead solve with 1 + 3 m right-hand sides (arrow_solve_multi),
+//   G = D^-1 + P^T (U H0^-1 U^T) P   over the 4 m pyramid rows (P: row -> n +- mu t; inactive rows are identity rows), SPD,
+//   d = y - Z P G^-1 P^T (U y)   (Woodbury).
+// m <= 2 takes this path; more simultaneous inter-agent contacts fall back to the dense elimination.
+#ifndef RS_WOODBURY
+#define RS_WOODBURY 1
+#endif
+// H0 X = R in place for NR vectors of NV floats (H0 = the compact arrowhead matrix of build_H_arrow)
+template <int LA, int LB, int NR>
+RS_HD void arrow_solve_multi(Ctx<LA, LB>& c, float* R) {
+    typedef Slab<LA, LB> S;
+    typedef Arrow<LA, LB> AR;
+    S& s = *c.s;
+    float* H = s.H;
+    RS_LANE_LOOP(g, S::LT) {
+        const float* Dg = H + AR::D0 + 3 * g; const float* B = H + AR::B0 + 12 * g;
+        float* W = H + AR::W0 + 12 * g;
+        const float idet = RS_RCP(fmaxf(Dg[0] * Dg[2] - Dg[1] * Dg[1], 1e-20f));
+        const float i00 = Dg[2] * idet, i01 = -Dg[1] * idet, i11 = Dg[0] * idet;
+        for (int k = 0; k < 6; k++) { W[2 * k] = B[2 * k] * i00 + B[2 * k + 1] * i01; W[2 * k + 1] = B[2 * k] * i01 + B[2 * k + 1] * i11; }
+    }
+    RS_LANE_LOOP(i, S::LT * NR) {       // Y = Dg^-1 rhs_g, over the leg entries of the vector
+        const int g = i / NR, j = i - g * NR;
+        const float* Dg = H + AR::D0 + 3 * g;
+        const float idet = RS_RCP(fmaxf(Dg[0] * Dg[2] - Dg[1] * Dg[1], 1e-20f));
+        const float i00 = Dg[2] * idet, i01 = -Dg[1] * idet, i11 = Dg[0] * idet;
+        float* v = R + j * S::NV + c.hipdof(g);
+        const float gh = v[0], ga = v[1];
+        v[0] = i00 * gh + i01 * ga; v[1] = i01 * gh + i11 * ga;
+    }
+    RS_SYNC();
+#if defined(__CUDA_ARCH__)
+    {   // Schur complement onto the two floating bases, 6 x (6 + NR) per agent with the rows in registers (lane 6 a + r)
+        const int lane = threadIdx.x & 31, a = lane >= 6 ? 1 : 0, r = lane - 6 * a;
+        const bool own = lane < 12;
+        float row[6 + NR];
+#pragma unroll
+        for (int cc = 0; cc < 6 + NR; cc++) row[cc] = 0.f;
+        if (own) {
+            const int l0 = c.leg0(a), va = c.vadr(a);
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++) row[cc] = H[AR::A0 + a * 36 + r * 6 + cc];
+#pragma unroll
+            for (int j = 0; j < NR; j++) row[6 + j] = R[j * S::NV + va + r];
+            RS_UNROLL1
+            for (int l = 0; l < c.L(a); l++) {
+                const float* W = H + AR::W0 + 12 * (l0 + l); const float* B = H + AR::B0 + 12 * (l0 + l);
+                const float w0 = W[2 * r], w1 = W[2 * r + 1], b0 = B[2 * r], b1 = B[2 * r + 1];
+#pragma unroll
+                for (int cc = 0; cc < 6; cc++) row[cc] -= w0 * B[2 * cc] + w1 * B[2 * cc + 1];
+                const float* Y = R + va + 6 + 2 * l;
+#pragma unroll
+                for (int j = 0; j < NR; j++) row[6 + j] -= b0 * Y[j * S::NV] + b1 * Y[j * S::NV + 1];
+            }
+        }
+        float diag = 1.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int src = own ? 6 * a + k : lane;
+            const float pk = __shfl_sync(0xffffffffu, row[k], src);
+            const float f = (r == k) ? 0.f : row[k] * RS_RCP(fmaxf(pk, 1e-12f));
+            if (r == k) diag = pk;
+#pragma unroll
+            for (int cc = k + 1; cc < 6 + NR; cc++) row[cc] = fmaf(-f, __shfl_sync(0xffffffffu, row[cc], src), row[cc]);
+        }
+        if (own) {
+            const float id = RS_RCP(fmaxf(diag, 1e-12f));
+#pragma unroll
+            for (int j = 0; j < NR; j++) R[j * S::NV + c.vadr(a) + r] = row[6 + j] * id;
+        }
+    }
+#else
+    for (int a = 0; a < 2; a++) {       // host emulation: the same elimination on a local copy
+        float Sx[6][6 + NR];
+        const int l0 = c.leg0(a), va = c.vadr(a);
+        for (int r = 0; r < 6; r++) {
+            for (int cc = 0; cc < 6; cc++) Sx[r][cc] = H[AR::A0 + a * 36 + r * 6 + cc];
+            for (int j = 0; j < NR; j++) Sx[r][6 + j] = R[j * S::NV + va + r];
+            for (int l = 0; l < c.L(a); l++) {
+                const float* W = H + AR::W0 + 12 * (l0 + l); const float* B = H + AR::B0 + 12 * (l0 + l);
+                for (int cc = 0; cc < 6; cc++) Sx[r][cc] -= W[2 * r] * B[2 * cc] + W[2 * r + 1] * B[2 * cc + 1];
+                const float* Y = R + va + 6 + 2 * l;
+                for (int j = 0; j < NR; j++) Sx[r][6 + j] -= B[2 * r] * Y[j * S::NV] + B[2 * r + 1] * Y[j * S::NV + 1];
+            }
+        }
+        for (int k = 0; k < 6; k++) {
+            float prow[6 + NR];
+            for (int cc = 0; cc < 6 + NR; cc++) prow[cc] = Sx[k][cc];
+            for (int r = 0; r < 6; r++) {
+                if (r == k) continue;
+                const float f = Sx[r][k] * RS_RCP(fmaxf(prow[k], 1e-12f));
+                for (int cc = k + 1; cc < 6 + NR; cc++) Sx[r][cc] = fmaf(-f, prow[cc], Sx[r][cc]);
+            }
+        }
+        for (int r = 0; r < 6; r++) for (int j = 0; j < NR; j++) R[j * S::NV + va + r] = Sx[r][6 + j] * RS_RCP(fmaxf(Sx[r][r], 1e-12f));
+    }
+#endif
+    RS_SYNC();
+    RS_LANE_LOOP(i, S::LT * NR) {       // back-substitution: d_g = Y - (B Dg^-1)^T d_t
+        const int g = i / NR, j = i - g * NR, a = c.agent_of_leg(g);
+        const float* W = H + AR::W0 + 12 * g;
+        float* v = R + j * S::NV + c.hipdof(g);
+        const float* dt = R + j * S::NV + c.vadr(a);
+        float dh_ = v[0], da_ = v[1];
+        for (int k = 0; k < 6; k++) { dh_ -= W[2 * k] * dt[k]; da_ -= W[2 * k + 1] * dt[k]; }
+        v[0] = dh_; v[1] = da_;
+    }
+    RS_SYNC();
+}
+
+// s.d = -H^-1 s.d with H = (arrowhead H0 already in s.H) + the m = s.wood_m inter-agent contacts s.wood_k[]
+template <int LA, int LB, int M>
+RS_HD void woodbury_solve(Ctx<LA, LB>& c) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    enum { K = 3 * M, NR = 1 + K, NA = 4 * M };
+    // scratch (alias zone, dead between the gradient and the end of the linear solve; build_H_arrow is done with it)
+    float* R = &s.tw[0][0];                    // [NR][NV]: -g, then the rows of U (afterwards y and Z)
+    float* UC = R + NR * S::NV;                // [M][16][4]: dof index, J n, J t1, J t2 of the 2 x 8 chain dofs (A side negated)
+    float* SM = UC + 64 * M;                   // [K][K + 1]: U Z | U y
+    float* G = s.H + Arrow<LA, LB>::S0;        // [NA][NA + 1]  (the tail of the H array, past the compact arrowhead matrix, W and Y)
+    static_assert(NR * S::NV + 64 * M + K * (K + 1) <= (int)S::ALIAS, "woodbury scratch must fit in the alias zone");
+    static_assert((int)Arrow<LA, LB>::S0 + NA * (NA + 1) <= (int)S::HDED, "woodbury G must fit behind the compact arrowhead matrix");
+    RS_LANE_LOOP(i, 16 * M) {
+        const int q = i >> 4, e = i & 15, k = s.wood_k[q];
+        const int b = e < 8 ? s.bA(k) : s.bB(k);
+        const V3 p = ld3(s.cpos[k]), n = ld3(s.cn[k]), t1 = ld3(s.ct1[k]);
+        int idx;
+        const V3 jc = (e < 8 ? -1.f : 1.f) * side_col(c, b, e & 7, p, false, &idx);
+        float* o = UC + 4 * i;
+        o[0] = (float)idx; o[1] = dot(jc, n); o[2] = dot(jc, t1); o[3] = dot(jc, cross(n, t1));
+    }
+    RS_LANE_LOOP(i, NR * S::NV) { R[i] = i < S::NV ? -s.d[i] : 0.f; }
+    RS_SYNC();
+    RS_LANE_LOOP(i, 16 * M) {
+        const int q = i >> 4;
+        const float* o = UC + 4 * i;
+        const int idx = (int)o[0];
+        if (idx >= 0) { for (int dir = 0; dir < 3; dir++) R[(1 + 3 * q + dir) * S::NV + idx] = o[1 + dir]; }
+    }
+    RS_SYNC();
+    arrow_solve_multi<LA, LB, NR>(c, R);
+    // U Z and U y: entry (i, j) = row i of U . solved vector j (j = K: y)
+    RS_LANE_LOOP(t, K * (K + 1)) {
+        const int i = t / (K + 1), j = t - i * (K + 1), q = i / 3, dir = i - 3 * q;
+        const float* x = R + (j < K ? 1 + j : 0) * S::NV;
+        const float* o = UC + 64 * q;
+        float acc = 0.f;
+        RS_UNROLL1
+        for (int e = 0; e < 16; e++) { const int idx = (int)o[4 * e]; if (idx >= 0) acc += o[4 * e + 1 + dir] * x[idx]; }
+        SM[t] = acc;
+    }
+    RS_SYNC();
+    // G = D^-1 + P^T S P over the pyramid rows (row (q, r): n + sg t1|t2); inactive rows are identity rows with zero right-hand side
+    RS_LANE_LOOP(t, NA * (NA + 1)) {
+        const int al = t / (NA + 1), be = t - al * (NA + 1);
+        const int qa = al >> 2, ra = al & 3, acta = (s.cact(s.wood_k[qa]) >> ra) & 1;
+        const int ia0 = 3 * qa, ia1 = 3 * qa + 1 + (ra >> 1);
+        const float sa = (ra & 1) ? -RS_MU : RS_MU;
+        float val;
+        if (be == NA) val = acta ? SM[ia0 * (K + 1) + K] + sa * SM[ia1 * (K + 1) + K] : 0.f;
+        else {
+            const int qb = be >> 2, rb = be & 3, actb = (s.cact(s.wood_k[qb]) >> rb) & 1;
+            const int ib0 = 3 * qb, ib1 = 3 * qb + 1 + (rb >> 1);
+            const float sb = (rb & 1) ? -RS_MU : RS_MU;
+            if (acta && actb)
+                val = SM[ia0 * (K + 1) + ib0] + sb * SM[ia0 * (K + 1) + ib1] + sa * SM[ia1 * (K + 1) + ib0] + sa * sb * SM[ia1 * (K + 1) + ib1]
+                      + (al == be ? RS_DIV(1.f, s.cD[s.wood_k[qa]]) : 0.f);
+            else val = al == be ? 1.f : 0.f;
+        }
+        G[t] = val;
+    }
+    RS_SYNC();
+    RS_UNROLL1
+    for (int k = 0; k < NA; k++) {       // Gauss-Jordan, lane = row (SPD: no pivoting)
+        RS_LANE_LOOP(al, NA) {
+            if (al != k) {
+                const float* prow = G + k * (NA + 1); float* arow = G + al * (NA + 1);
+                const float f = arow[k] * RS_RCP(fmaxf(prow[k], 1e-20f));
+                for (int cc = k + 1; cc <= NA; cc++) arow[cc] = fmaf(-f, prow[cc], arow[cc]);
+            }
+        }
+        RS_SYNC();
+    }
+    // d = y - Z P w
+    RS_LANE_LOOP(i, S::NV) {
+        float acc = R[i];
+        RS_UNROLL1
+        for (int q = 0; q < M; q++) {
+            float w[4];
+            for (int r = 0; r < 4; r++) w[r] = G[(4 * q + r) * (NA + 1) + NA] * RS_RCP(fmaxf(G[(4 * q + r) * (NA + 1) + 4 * q + r], 1e-20f));
+            acc -= (w[0] + w[1] + w[2] + w[3]) * R[(1 + 3 * q) * S::NV + i] + RS_MU * (w[0] - w[1]) * R[(2 + 3 * q) * S::NV + i] + RS_MU * (w[2] - w[3]) * R[(3 + 3 * q) * S::NV + i];
+        }
+        s.d[i] = acc;
     }
     RS_SYNC();
 }
@@ -1422,13 +1622,24 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
             RS_ATOMIC_OR(&s.coupled, ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1 : 2);
     }
     RS_SYNC();
+    if (RS_UNLIKELY(s.coupled == 1)) {      // inter-agent contacts only: list the active ones (fixed order) for the low-rank path
+        if (RS_LANE0) {
+            int m = 0;
+            for (int k = 0; k < s.ncon; k++) if (s.bA(k) >= 0 && s.cact(k) != 0) { if (m < 2) s.wood_k[m] = k; m++; }
+            s.wood_m = m;
+        }
+        RS_SYNC();
+    }
     jt_forces(c);
     RS_LANE_LOOP(i, S::NV) { s.d[i] = s.r[i] - s.jtf[i]; }     // gradient
     RS_SYNC();
     RS_ACC(0);
-    if (RS_LIKELY(RS_ARROW && s.coupled == 0)) build_H_arrow(c); else build_H(c);
+    const bool wood = RS_WOODBURY && RS_ARROW && s.coupled == 1 && s.wood_m <= 2;
+    if (RS_LIKELY(RS_ARROW && (s.coupled == 0 || wood))) build_H_arrow(c); else build_H(c);
     RS_ACC(1);
-    if (RS_LIKELY(RS_ARROW && s.coupled == 0)) arrow_solve(c); else chol_solve(c);      // s.d = -H^-1 grad
+    if (RS_LIKELY(RS_ARROW && s.coupled == 0)) arrow_solve(c);      // s.d = -H^-1 grad
+    else if (wood) { if (s.wood_m == 1) woodbury_solve<LA, LB, 1>(c); else woodbury_solve<LA, LB, 2>(c); }
+    else chol_solve(c);
     RS_ACC(2);
     twists(c, s.d);
     rows_of(c, s.d, s.cjd, s.ljd);

@@ -161,3 +161,28 @@ def test_leg_straddling_the_tatami_edge(emu, oracle_models):
         assert abs(qacc - r['qacc']).max() <= 3e-4 * max(1.0, abs(r['qacc']).max()), trial
         n_checked += 1
     assert n_edge >= 10 and n_checked == n_edge
+
+
+def test_inter_agent_contacts_low_rank_and_dense_paths(emu, oracle_models):
+    """Agents pressed against each other: one or two inter-agent contacts take the low-rank (Woodbury) correction of the arrowhead
+    solve, three or more the dense elimination.  Both must reproduce the float64 oracle's accelerations, and the sample must
+    exercise both paths."""
+    om = oracle_models('ant'); ps = PairSpec('ant', 'ant')
+    rng = np.random.RandomState(17)
+    seen = {1: 0, 2: 0, 3: 0}
+    for spread in (0.3, 0.4, 0.5, 0.6):
+        qs, vs = settled_states(om, rng, 6, steps=25, action_scale=0.4, spread=spread)
+        for q, v in zip(qs, vs):
+            ctrl = rng.uniform(-1, 1, om.nu)
+            r = om.forward(q, v, ctrl, full=True)
+            qf = np.array(q, np.float32); vf = np.array(v, np.float32); cf = np.array(ctrl, np.float32)
+            qacc = np.zeros(ps.nv, np.float32); con = np.zeros((64, 8), np.float32)
+            ncon, nit = ctypes.c_int(), ctypes.c_int()
+            st = emu.emu_forward(ps.pack(), ctypes.c_float(0.01), 16, P(qf), P(vf), P(cf), P(qacc), None, None,
+                                 ctypes.byref(ncon), ctypes.byref(nit), P(con), None)
+            assert st == 0 and ncon.value == r['ncon']
+            m = int((con[:ncon.value, 7] >= 0).sum())            # bA * 100 + bB with bA = -1 for the world
+            if m:
+                seen[min(m, 3)] += 1
+            assert abs(qacc - r['qacc']).max() <= 2e-4 * max(1.0, abs(r['qacc']).max()), (spread, m)
+    assert seen[1] > 0 and seen[2] > 0 and seen[3] > 0, seen

@@ -17,6 +17,7 @@ from collections import defaultdict
 
 rep, lib = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else 'k_stepILi4ELi4'
+LINES_OF = sys.argv[4] if len(sys.argv) > 4 else None      # optional: per-source-line table of this function (its own frame in the inline chain)
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 
 
@@ -84,6 +85,7 @@ body = [r for r in rows[h + 1:] if len(r) == len(hdr)]
 base = int(body[0][0], 16)
 stalls = [n for n in hdr if n.startswith('stall_') and '(Not Issued)' not in n]
 agg_in, agg_out = defaultdict(lambda: defaultdict(float)), defaultdict(lambda: defaultdict(float))
+by_line = defaultdict(lambda: defaultdict(float))
 tot = defaultdict(float)
 for r in body:
     off = int(r[0], 16) - base
@@ -99,6 +101,11 @@ for r in body:
         outer = 'solve_first'
     ex = float(r[col['Instructions Executed']] or 0); thr = float(r[col['Thread Instructions Executed']] or 0)
     smp = float(r[col['# Samples']] or 0)
+    if LINES_OF:
+        for f, ln in ch:
+            if fn_of(f, ln) == LINES_OF:
+                by_line[ln]['exec'] += ex; by_line[ln]['thr'] += thr; by_line[ln]['sass'] += 1; by_line[ln]['samples'] += smp - float(r[col['stall_barrier']] or 0)
+                break
     for A, key in ((agg_in, inner), (agg_out, outer)):
         A[key]['exec'] += ex; A[key]['thr'] += thr; A[key]['samples'] += smp; A[key]['sass'] += 1
         for s in stalls:
@@ -118,3 +125,9 @@ for title, A in (('by innermost function', agg_in), ('by phase (outermost functi
             k, 100 * v['exec'] / tot['exec'], 100 * v['samples'] / tot['samples'], 100 * nb / nb_tot, v['thr'] / max(v['exec'], 1), v['sass'],
             100 * v['stall_wait'] / max(nb, 1), 100 * v['stall_short_sb'] / max(nb, 1), 100 * v['stall_not_selected'] / max(nb, 1),
             100 * v['stall_no_inst'] / max(nb, 1), 100 * v['stall_branch_resolving'] / max(nb, 1), 100 * v['stall_mio'] / max(nb, 1)))
+
+if LINES_OF:
+    src = open(os.path.join(ROOT, 'robosumo_selfplay_b200/csrc/rs_core.h')).read().split('\n')
+    print('\nlines of %s (warp-instructions executed per pair-step assuming 4096 pairs, lanes, distinct SASS, non-barrier samples)' % LINES_OF)
+    for ln, v in sorted(by_line.items()):
+        print('%5d %8.0f %5.1f %5d %6.0f | %s' % (ln, v['exec'] / 4096, v['thr'] / max(v['exec'], 1), v['sass'], v['samples'], src[ln - 1].strip()[:110]))
