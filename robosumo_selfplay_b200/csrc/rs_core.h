@@ -1364,8 +1364,7 @@ RS_HD void woodbury_solve(Ctx<LA, LB>& c) {
         const float* x = R + (j < K ? 1 + j : 0) * S::NV;
         const float* o = UC + 64 * q;
         float acc = 0.f;
-        RS_UNROLL1
-        for (int e = 0; e < 16; e++) { const int idx = (int)o[4 * e]; if (idx >= 0) acc += o[4 * e + 1 + dir] * x[idx]; }
+        for (int e = 0; e < 16; e++) { const int idx = (int)o[4 * e]; acc += idx >= 0 ? o[4 * e + 1 + dir] * x[idx] : 0.f; }      // (unrolled: the loads overlap)
         SM[t] = acc;
     }
     RS_SYNC();
