@@ -60,6 +60,8 @@ struct EnvDev {
     float *qpos, *qvel, *warm, *ep_ret, *ep_dret;
     int* pred;                         // active-set prediction carried across steps: [E][4 + MAXC/2] = limit masks (non-zero, negative side, loaded), nprev, cprev pairs
     int* latch;                        // [2]: OR of every status bit any env raised since the last rs_status_latch(clear) -- auto-reset does not clear it; number of env-steps that raised one
+    int* next;                         // [2] pair counters of the persistent k_step (this launch: next[tick], cleared for the next one)
+    int tick;
     int *ep_step, *status, *diag;      // diag[E][4]: Newton iterations, coupled evaluations, contacts summed over the last env step, max iterations of one evaluation
     unsigned int* ep_count;
     const rs_agent_model* am;
@@ -81,6 +83,7 @@ struct rs_env {
     cudaStream_t stream;
     size_t smem;
     int wpb;      // warps (env pairs) per block: as many slabs as fit in one SM's shared memory, at most RS_WPB
+    int sms;      // multiprocessors of the device (grid of the persistent k_step)
 };
 
 template <int LA, int LB>
@@ -191,35 +194,16 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_set_state(EnvDev d, const float
     if (obs) env_write_obs(c, obs + (size_t)e * OD, tsfeat(d.ep_step[e]));
 }
 
+// everything of an env step behind the physics, for the pair in this warp's slab: mj_checkPos / mj_checkVel analogue, rewards and
+// flags, episode bookkeeping, auto-reset, observation
 template <int LA, int LB>
-__global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __restrict__ actions, float* __restrict__ obs,
-                                                       float* __restrict__ rew, uint8_t* __restrict__ done,
-                                                       float* __restrict__ info, float* __restrict__ episode, int auto_reset) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ rs_agent_model sm_am[2];
+__device__ __forceinline__ void pair_finish(Ctx<LA, LB>& c, const EnvDev& d, int e, const float* before, const float* __restrict__ actions,
+                                            float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                                            float* __restrict__ info, float* __restrict__ episode, int auto_reset, bool live) {
     typedef Slab<LA, LB> S;
-    Ctx<LA, LB> c;
-    warp_setup(c, d, sm_am, smem_raw);
-    int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-#ifdef RS_LOCKSTEP
-    const bool live = e < d.E;       // surplus warps of the last block shadow the last env (they must reach the block barriers)
-    if (!live) e = d.E - 1;
-#else
-    const bool live = true;
-    if (e >= d.E) return;
-#endif
     S& s = *c.s;
     const int lane = threadIdx.x & 31;
-    load_state(c, d, e);
     const float* act = actions + (size_t)e * S::NU;
-    set_act(c, act);
-    float before[4] = { s.q[c.qadr(0)], s.q[c.qadr(0) + 1], s.q[c.qadr(1)], s.q[c.qadr(1) + 1] };
-    RS_SYNC();
-#ifdef RS_EXPERIMENT_CLOCK
-    c.evk = 0; c.env = e; for (int i = 0; i < 6; i++) c.acc[i] = 0; c.tlast = rs_clock(); if (lane == 0) rs_dbg[(size_t)e * 128 + 60] = rs_clock();
-#endif
-    simulate(c, d.P.frame_skip);
-    // mj_checkPos / mj_checkVel analogue
     {
         bool bad = false;
         RS_LANE_LOOP(i, S::NQ) { if (!isfinite(s.q[i])) bad = true; }
@@ -257,6 +241,63 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
         store_state(c, d, e);
         if (lane == 0) { d.ep_step[e] = num_steps; d.ep_ret[e] = er; d.ep_dret[e] = edr; d.status[e] = st | (o.done[0] ? 8 : 0); }
         env_write_obs(c, obs + (size_t)e * OD, tsfeat(num_steps));
+    }
+    RS_SYNC();
+}
+
+template <int LA, int LB>
+__device__ __forceinline__ void pair_begin(Ctx<LA, LB>& c, const EnvDev& d, int e, const float* __restrict__ actions, float* before) {
+    typedef Slab<LA, LB> S;
+    S& s = *c.s;
+    load_state(c, d, e);
+    set_act(c, actions + (size_t)e * S::NU);
+    before[0] = s.q[c.qadr(0)]; before[1] = s.q[c.qadr(0) + 1]; before[2] = s.q[c.qadr(1)]; before[3] = s.q[c.qadr(1) + 1];
+    RS_SYNC();
+#ifdef RS_EXPERIMENT_CLOCK
+    c.evk = 0; c.env = e; for (int i = 0; i < 6; i++) c.acc[i] = 0; c.tlast = rs_clock(); if ((threadIdx.x & 31) == 0) rs_dbg[(size_t)e * 128 + 60] = rs_clock();
+#endif
+}
+
+// Ant pairs (the per-trip re-alignment of simulate_trips): PERSISTENT blocks, one per SM.  A warp that finishes its pair writes the
+// pair's outputs and takes the next pair off a device-wide counter while the rest of the block carries on, so with several pairs per
+// warp slot nobody idles until the slowest pair of a block of 28 is through (that wait was a third of the block time); with at
+// most one pair per slot (E <= SMs x 28) it degenerates to one pair per warp.  The counter of the NEXT launch is cleared here
+// (launches of one env are stream-ordered).  Other morphologies: one pair per warp, re-aligned per evaluation.
+template <int LA, int LB>
+__global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __restrict__ actions, float* __restrict__ obs,
+                                                       float* __restrict__ rew, uint8_t* __restrict__ done,
+                                                       float* __restrict__ info, float* __restrict__ episode, int auto_reset) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ rs_agent_model sm_am[2];
+    typedef Slab<LA, LB> S;
+    Ctx<LA, LB> c;
+    warp_setup(c, d, sm_am, smem_raw);
+    float before[4];
+    if constexpr (RS_TRIP_MACHINE && LA + LB <= 8) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) d.next[d.tick ^ 1] = 0;
+        int e = -1;
+        simulate_trips(c, d.P.frame_skip, [&](bool finish) -> bool {
+            if (finish) pair_finish(c, d, e, before, actions, obs, rew, done, info, episode, auto_reset, true);
+            int ne = 0;
+            if ((threadIdx.x & 31) == 0) ne = atomicAdd(d.next + d.tick, 1);
+            ne = __shfl_sync(0xffffffffu, ne, 0);
+            if (ne >= d.E) return false;
+            e = ne;
+            pair_begin(c, d, e, actions, before);
+            return true;
+        });
+    } else {
+        int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#ifdef RS_LOCKSTEP
+        const bool live = e < d.E;       // surplus warps of the last block shadow the last env (they must reach the block barriers)
+        if (!live) e = d.E - 1;
+#else
+        const bool live = true;
+        if (e >= d.E) return;
+#endif
+        pair_begin(c, d, e, actions, before);
+        simulate(c, d.P.frame_skip);
+        pair_finish(c, d, e, before, actions, obs, rew, done, info, episode, auto_reset, live);
     }
 }
 
@@ -332,6 +373,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
         // scheduler backfills finished SMs anyway.)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        h->sms = sms;
         const long long E = cfg->num_envs;
         if (E <= (long long)sms * h->wpb) { const int even = (int)((E + sms - 1) / sms); if (even >= 1 && even < h->wpb) h->wpb = even; }
     }
@@ -353,6 +395,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
     CUDA_OK(cudaMalloc(&d.status, sizeof(int) * E)); CUDA_OK(cudaMalloc(&d.ep_count, sizeof(unsigned int) * E));
     CUDA_OK(cudaMalloc(&d.diag, sizeof(int) * E * 4)); CUDA_OK(cudaMemset(d.diag, 0, sizeof(int) * E * 4));
     CUDA_OK(cudaMalloc(&d.latch, sizeof(int) * 2)); CUDA_OK(cudaMemset(d.latch, 0, sizeof(int) * 2));
+    CUDA_OK(cudaMalloc(&d.next, sizeof(int) * 2)); CUDA_OK(cudaMemset(d.next, 0, sizeof(int) * 2)); d.tick = 0;
     CUDA_OK(cudaMemset(d.qpos, 0, sizeof(float) * E * h->nq)); CUDA_OK(cudaMemset(d.qvel, 0, sizeof(float) * E * h->nv));
     CUDA_OK(cudaMemset(d.warm, 0, sizeof(float) * E * h->nv)); CUDA_OK(cudaMemset(d.ep_ret, 0, sizeof(float) * E));
     CUDA_OK(cudaMemset(d.ep_dret, 0, sizeof(float) * E)); CUDA_OK(cudaMemset(d.ep_step, 0, sizeof(int) * E));
@@ -382,7 +425,7 @@ int rs_create(const rs_config* cfg, const rs_agent_model* agents, rs_env** out) 
 void rs_destroy(rs_env* h) {
     if (!h) return;
     cudaFree(h->d_am); cudaFree(h->d.qpos); cudaFree(h->d.qvel); cudaFree(h->d.warm); cudaFree(h->d.pred); cudaFree(h->d.ep_ret);
-    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.diag); cudaFree(h->d.latch); cudaFree(h->d.status); cudaFree(h->d.ep_count);
+    cudaFree(h->d.ep_dret); cudaFree(h->d.ep_step); cudaFree(h->d.diag); cudaFree(h->d.latch); cudaFree(h->d.next); cudaFree(h->d.status); cudaFree(h->d.ep_count);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_epi); cudaFreeHost(h->h_done);
     cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_epi); cudaFree(h->s_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -434,7 +477,14 @@ int rs_step(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* do
             int auto_reset, void* stream) {
     if (!h || !actions || !obs || !rew || !done) return fail(RS_ERR_ARG, "rs_step: bad argument%s", "");
     return dispatch(h, [&](auto la, auto lb) {
-        k_step<decltype(la)::value, decltype(lb)::value><<<GRID(h)>>>(h->d, actions, obs, rew, done, info, episode, auto_reset);
+        constexpr int A = decltype(la)::value, B = decltype(lb)::value;
+        if (RS_TRIP_MACHINE && A + B <= 8) {      // persistent blocks, pairs handed out by a device counter
+            int grid = (h->d.E + h->wpb - 1) / h->wpb;
+            if (grid > h->sms) grid = h->sms;
+            k_step<A, B><<<grid, 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->d, actions, obs, rew, done, info, episode, auto_reset);
+            h->d.tick ^= 1;
+        } else
+            k_step<A, B><<<GRID(h)>>>(h->d, actions, obs, rew, done, info, episode, auto_reset);
         g_launches++;
         CUDA_OK(cudaGetLastError());
         return RS_OK;

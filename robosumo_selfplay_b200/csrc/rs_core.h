@@ -1823,14 +1823,13 @@ RS_HD void substep_begin(Ctx<LA, LB>& c) {
 // block re-aligns once per TRIP = [start of an evaluation, for the warps that begin one] + [one Newton iteration, every warp]:
 // a pair that needs an extra iteration simply starts its next evaluation one trip later, nobody waits for its whole tail, and a
 // block is finished after max-over-pairs(total iterations of the step) trips instead of sum-over-evaluations(max-over-pairs).
-template <int LA, int LB>
-RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
-    // measured at E = 4096 (tools/bench_morphologies.py): Ant 1.65 -> 1.61 ms per trip, Bug 5.01 -> 5.06 (equal), Spider 7.56 -> 8.11:
-    // the larger bodies have 19 / 15 warps per block (bigger slabs) and less to gain from not waiting, so they keep the
-    // per-evaluation re-alignment
-    if constexpr (RS_TRIP_MACHINE && LA + LB <= 8) {
+// next_pair(finish): finish the pair in the slab (finish = true: write its outputs) and load the next one; false = none left.
+// (Measured and dropped: changing pairs in the first half of the next trip, beside the evaluation starts of the other warps -- equal.)
+template <int LA, int LB, typename NextPair>
+RS_HD void simulate_trips(Ctx<LA, LB>& c, int nsub, NextPair next_pair) {
     int sub = 0, st = 0, it = 0;
-    bool fresh = true, done = nsub <= 0;
+    bool fresh = true, done = !next_pair(false);
+    if (nsub <= 0) { while (!done) done = !next_pair(true); }
     if (!done) substep_begin(c);
     while (RS_TRIP_ANY(!done)) {
         if (!done && fresh) { eval_begin(c); it = 0; fresh = false; }
@@ -1844,10 +1843,23 @@ RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
                 RS_CLOCK_END();
                 rk_after_eval(c, st);
                 fresh = true;
-                if (++st == 4) { st = 0; if (++sub == nsub) done = true; else substep_begin(c); }
+                if (++st == 4) {
+                    st = 0;
+                    if (++sub == nsub) { sub = 0; done = !next_pair(true); }
+                    if (!done) substep_begin(c);
+                }
             }
         }
     }
+}
+template <int LA, int LB>
+RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
+    // measured at E = 4096 (tools/bench_morphologies.py): Ant 1.65 -> 1.61 ms per trip, Bug 5.01 -> 5.06 (equal), Spider 7.56 -> 8.11:
+    // the larger bodies have 19 / 15 warps per block (bigger slabs) and less to gain from not waiting, so they keep the
+    // per-evaluation re-alignment
+    if constexpr (RS_TRIP_MACHINE && LA + LB <= 8) {
+        bool first = true;
+        simulate_trips(c, nsub, [&](bool) -> bool { const bool r = first; first = false; return r; });       // the one pair already in the slab
     } else {
     for (int sub = 0; sub < nsub; sub++) {
         RS_SUBSTEP_SYNC();
