@@ -61,7 +61,7 @@ struct EnvDev {
     int* pred;                         // active-set prediction carried across steps: [E][4 + MAXC/2] = limit masks (non-zero, negative side, loaded), nprev, cprev pairs
     int* latch;                        // [2]: OR of every status bit any env raised since the last rs_status_latch(clear) -- auto-reset does not clear it; number of env-steps that raised one
     int* next;                         // [2] pair counters of the persistent k_step (this launch: next[tick], cleared for the next one)
-    int tick;
+    int tick, persistent;
     int *ep_step, *status, *diag;      // diag[E][4]: Newton iterations, coupled evaluations, contacts summed over the last env step, max iterations of one evaluation
     unsigned int* ep_count;
     const rs_agent_model* am;
@@ -91,7 +91,7 @@ __device__ __forceinline__ Slab<LA, LB>* warp_setup(Ctx<LA, LB>& c, const EnvDev
     typedef Slab<LA, LB> S;
     for (int i = threadIdx.x; i < (int)(2 * sizeof(rs_agent_model) / 4); i += blockDim.x) ((int*)sm_am)[i] = ((const int*)d.am)[i];
     __syncthreads();
-    S* s = reinterpret_cast<S*>(smem_raw) + (threadIdx.x >> 5);
+    S* s = reinterpret_cast<S*>(smem_raw) + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform on purpose: cheaper to keep / rebuild than a per-lane value (-1.7 % step time)
     c.s = s; c.am = sm_am; c.h = d.h; c.max_newton = d.max_newton;
     return s;
 }
@@ -279,8 +279,10 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
         simulate_trips(c, d.P.frame_skip, [&](bool finish) -> bool {
             if (finish) pair_finish(c, d, e, before, actions, obs, rew, done, info, episode, auto_reset, true);
             int ne = 0;
-            if ((threadIdx.x & 31) == 0) ne = atomicAdd(d.next + d.tick, 1);
-            ne = __shfl_sync(0xffffffffu, ne, 0);
+            if (d.persistent) {
+                if ((threadIdx.x & 31) == 0) ne = atomicAdd(d.next + d.tick, 1);
+                ne = __shfl_sync(0xffffffffu, ne, 0);
+            } else ne = finish ? d.E : (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));      // one wave: one pair per warp
             if (ne >= d.E) return false;
             e = ne;
             pair_begin(c, d, e, actions, before);
@@ -480,6 +482,7 @@ int rs_step(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* do
         constexpr int A = decltype(la)::value, B = decltype(lb)::value;
         if (RS_TRIP_MACHINE && A + B <= 8) {      // persistent blocks, pairs handed out by a device counter
             int grid = (h->d.E + h->wpb - 1) / h->wpb;
+            h->d.persistent = grid > h->sms ? 1 : 0;
             if (grid > h->sms) grid = h->sms;
             k_step<A, B><<<grid, 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->d, actions, obs, rew, done, info, episode, auto_reset);
             h->d.tick ^= 1;

@@ -75,6 +75,57 @@ def test_trajectory_parity_20_env_steps(oracle_models):
         assert int((status & 7).max()) == 0
 
 
+def test_full_size_oracle_anchor_4096(oracle_models):
+    """BASELINE.json's full size (4096 pairs, one persistent-kernel launch per step) anchored on the oracle: 64 pairs sampled from
+    the batch -- first, last, the block boundaries of the 28-pairs-per-block layout, and random ones -- must follow the float64
+    oracle stepped from the same reset states with the same actions (tolerances of the small-batch trajectory test).
+
+    The dynamics has discrete events (a contact entering the 0.01 margin with a closing velocity changes the force by a finite
+    amount), so a pair that passes within float32 rounding of such an event can take the other branch: with seed 1, pair 3541 lands
+    |dv| = 0.12 away from the oracle at step 6 -- and so does the ORACLE ITSELF when its initial state is perturbed by 1e-6
+    (half of the perturbed runs).  Such a pair is accepted only if the oracle reaches the kernel's state from an initial state
+    within 1e-6 of the same start; at most 3 of the 64 pairs may need that."""
+    import torch
+    om = oracle_models('ant')
+    E = 4096
+    env = make_env(E, device_api=True, auto_reset=False)
+    env.reset()
+    q0, v0, _, _ = env.get_state()
+    rng = np.random.RandomState(4)
+    pick = np.unique(np.concatenate([[0, 1, 27, 28, 29, 55, 56, 4087, 4088, 4094, 4095], rng.choice(E, 53, replace=False)]))
+    qi = q0.double().cpu().numpy()[pick]; vi = v0.double().cpu().numpy()[pick]
+    T = 6
+    acts = 0.7 * rng.randn(T, E, 2, 8)
+
+    def oracle_run(q, v, e):
+        q = q.copy(); v = v.copy(); w = np.zeros(om.nv)
+        for t in range(T):
+            om.step(q, v, acts[t, e].ravel(), 5, w)
+        return q, v
+
+    for t in range(T):
+        env.step(torch.as_tensor(acts[t], dtype=torch.float32, device='cuda'))
+    gq, gv, _, status = env.get_state()
+    assert int(status.max()) & 7 == 0
+    gq = gq.double().cpu().numpy()[pick]; gv = gv.double().cpu().numpy()[pick]
+    branch = 0
+    for i, e in enumerate(pick):
+        q, v = oracle_run(qi[i], vi[i], e)
+        if abs(gq[i] - q).max() < 2e-4 and abs(gv[i] - v).max() < 5e-3:
+            continue
+        branch += 1
+        prng = np.random.RandomState(100 + i)
+        best = np.inf
+        for k in range(24):
+            qp = qi[i] + 1e-6 * prng.randn(om.nq); om.normalize_qpos(qp)
+            q, v = oracle_run(qp, vi[i], e)
+            if abs(gq[i] - q).max() < 2e-4:
+                best = min(best, abs(gv[i] - v).max())
+        assert best < 5e-3, (int(e), best)
+    assert branch <= 3, branch
+    env.close()
+
+
 def test_full_size_invariants_4096():
     """Size-independent properties at BASELINE config 2 (E=4096): unit quaternions, finite state,
     joint angles near their ranges, torsos above the floor, no status flags, obs layout."""

@@ -93,9 +93,9 @@ for r in body:
     inner = fn_of(*ch[0]) if ch else '?'
     # phase = first frame below the drivers (kernel body, simulate, eval_begin, solve_iter, ...), walking from the outside in
     names = [fn_of(f, ln) for f, ln in ch][::-1]
-    drivers = ('__launch_bounds__', 'simulate', 'eval_begin', 'forward', 'solve', 'solve_iter', 'rs_api.cu:outer')
+    drivers = ('__launch_bounds__', 'simulate', 'simulate_trips', 'eval_begin', 'forward', 'solve', 'solve_iter', 'rs_api.cu:outer')
     outer = next((n for n in names if n not in drivers), names[-1] if names else '?')
-    if outer != '?' and 'solve_iter' in names and outer not in ('jt_forces', 'build_H_arrow', 'build_H', 'arrow_solve', 'chol_solve', 'gj_rows_in_registers', 'line_search'):
+    if outer != '?' and 'solve_iter' in names and outer not in ('jt_forces', 'build_H_arrow', 'build_H', 'arrow_solve', 'chol_solve', 'gj_rows_in_registers', 'line_search', 'woodbury_solve', 'arrow_solve_multi'):
         outer = 'iter:' + outer if outer in ('twists', 'rows_of', 'mat_vec') else ('solve_iter' if names[-1] == 'solve_iter' or outer in ('ld3', 'v3', 'dot', 'cross') else outer)
     if 'solve_first' in names:
         outer = 'solve_first'
