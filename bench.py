@@ -255,6 +255,8 @@ def measure_learner(args, E, local, rank, world, dev):
     torch.cuda.synchronize()
     upd_loop_s = time.perf_counter() - t0
     upd_gpu_s = e0.elapsed_time(e1) / 1e3
+    model.check_peer()
+    allreduce = 'none (1 GPU)' if comm is None else ('rs_peer_allreduce: one kernel over NVLink peer memory on the learner stream' if model._peer_h not in (None, False) else 'torch.distributed all_reduce (NCCL)')
     tt = torch.tensor([roll_s, upd_s, upd_loop_s, upd_gpu_s], dtype=torch.float64, device=dev)
     if comm is not None:
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)          # max over ranks
@@ -266,9 +268,9 @@ def measure_learner(args, E, local, rank, world, dev):
             'ppo_update': {'value': upd_loop_s, 'unit': 's/iter', 'samples': N, 'nminibatches': nmb, 'noptepochs': nep, 'minibatch': nbt,
                            'higher_is_better': False, 'dtype': 'tf32 GEMMs (tcgen05) + f32', 'achieved_tflops': flops / upd_loop_s / 1e12,
                            'achieved_gbs': 536.0 * N * nep / upd_loop_s / 1e9, 'launches_per_minibatch': upd_launches / float(nmb * nep),
-                           'gpu_seconds': upd_gpu_s,
+                           'gpu_seconds': upd_gpu_s, 'gradient_allreduce': allreduce,
                            'standalone': {'value': upd_s, 'unit': 's/iter', 'note': 'same update started cold: includes the host-side replay of the six legacy NumPy shuffles over all %d GLOBAL indices (bit-exact schedule, one epoch ahead of the GPU) on the critical path' % N},
-                           'note': 'as alg_ppo.learn runs it (max over ranks): V-trace is part of the rollout; the six permutations are drawn by the helper thread during the preceding rollout; per epoch one H2D of the int32 permutation, one device-side split + advantage-moment launch (one all-reduce per epoch when N > 1), per minibatch 3 launches and ONE gradient all-reduce'}}
+                           'note': 'as alg_ppo.learn runs it (max over ranks): V-trace is part of the rollout; the six permutations are drawn by the helper thread during the preceding rollout; per epoch one H2D of the int32 permutation, one device-side split + advantage-moment launch (one all-reduce per epoch when N > 1), per minibatch 3 launches and ONE gradient all-reduce (N > 1: a 4th launch, the peer-memory all-reduce kernel)'}}
 
 
 def measure_config1_ref_shape(local, dev):

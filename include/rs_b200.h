@@ -179,6 +179,24 @@ int rs_seed(rs_env* h, unsigned long long seed);
  * the 20 forward evaluations of the step, and the largest iteration count of a single evaluation (cf. mjData.solver_iter / ncon) */
 int rs_get_diag(rs_env* h, int* diag, void* stream);
 
+/* ---- gradient all-reduce over NVLink peer memory (one node, one process per GPU) -----------------------------------------------
+ * Replaces the torch.distributed / NCCL all-reduce of the flat gradient(+stats) inside a minibatch step (the pattern of
+ * baselines/baselines/common/mpi_adam_optimizer.py:21-46) with ONE kernel on the learner's own stream: every rank owns a
+ * double-buffered symmetric buffer that its peers map through CUDA IPC; rs_ppo_grad writes the local gradient into
+ * rs_peer_send_buffer(), rs_peer_allreduce then (1) raises this rank's step counter in every peer's flag array, (2) waits for the
+ * peers' counters and (3) sums the `nfloats` entries over the ranks in rank order (bit-identical on every rank) into `out`.
+ * No host synchronisation and no second stream; a peer that never arrives makes the kernel give up after ~2 s and latches an
+ * error that rs_peer_error() reports.  Handles are exchanged by the caller (dist.py: one all_gather of rs_peer_handle_bytes()). */
+typedef struct rs_peer rs_peer;
+int rs_peer_create(int rank, int world, long long nfloats, int device, rs_peer** out);
+int rs_peer_handle_bytes(void);
+int rs_peer_export(rs_peer* p, void* handle_out);
+int rs_peer_connect(rs_peer* p, const void* all_handles);          /* [world][rs_peer_handle_bytes()] in rank order */
+float* rs_peer_send_buffer(rs_peer* p);                            /* where the NEXT rs_peer_allreduce expects this rank's data */
+int rs_peer_allreduce(rs_peer* p, float* out, long long nfloats, void* stream);
+int rs_peer_error(rs_peer* p);                                     /* non-zero after a timed-out wait (synchronises the device) */
+void rs_peer_destroy(rs_peer* p);
+
 /* single-GPU convenience: [rs_adv_moments ->] rs_ppo_grad -> rs_adam_step in ONE call, 3 launches (a data-parallel caller uses the
  * pieces and all-reduces grad_stats between them).  beta1 = 0.9, beta2 = 0.999, eps = 1e-5 as model.py:121; adv_sums [2] doubles
  * (already filled when moments_ready != 0, e.g. by rs_adv_moments_multi) and grad_stats [P + 8] floats are caller-owned device buffers. */

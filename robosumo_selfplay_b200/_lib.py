@@ -68,6 +68,14 @@ SYMBOLS = {
     'rs_seed': (c_int, [c_void_p, ctypes.c_ulonglong]),
     'rs_legacy_shuffle': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong]),
     'rs_ppo_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
+    'rs_peer_create': (c_int, [c_int, c_int, ctypes.c_longlong, c_int, ctypes.POINTER(c_void_p)]),
+    'rs_peer_handle_bytes': (c_int, []),
+    'rs_peer_export': (c_int, [c_void_p, c_void_p]),
+    'rs_peer_connect': (c_int, [c_void_p, c_void_p]),
+    'rs_peer_send_buffer': (c_void_p, [c_void_p]),
+    'rs_peer_allreduce': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    'rs_peer_error': (c_int, [c_void_p]),
+    'rs_peer_destroy': (None, [c_void_p]),
 }
 
 

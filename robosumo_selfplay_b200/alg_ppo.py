@@ -388,6 +388,8 @@ def learn(*, network='mlp', env, total_timesteps, eval_env=None, opponent_mode='
                 break
         perms.close()
         lossvals = torch.stack(stat_acc).double().mean(0).cpu().numpy().tolist()          # np.mean(mblossvals, axis=0)
+        if hasattr(model, 'check_peer'):
+            model.check_peer()                              # a rank that missed a peer all-reduce (time-out) means diverged replicas: raise
         ratio_log['approxkl'].append(float(lossvals[3])); ratio_log['ppo_clip_frac'].append(float(lossvals[4]))
         if rank == 0 and log_dir and opponent_mode == 'random' and (update % 100 == 0 or update == 1):
             import pickle

@@ -782,6 +782,113 @@ int rs_ppo_minibatch_step(float* params, float* m, float* v, int obs_dim, int ac
     return rs_adam_step(params, m, v, grad_stats, obs_dim, act_dim, ent_coef, max_grad_norm, lr, step_t, 0.9f, 0.999f, 1e-5f, gnorm_out, n, stats5, stream);
 }
 
+}  // extern "C"
+
+// ---- gradient all-reduce over NVLink peer memory ---------------------------------------------------------------------------
+#define RS_PEER_MAX 16
+struct rs_peer {
+    int rank, world, device;
+    long long nfloats, step;
+    float* buf;                     // [2][nfloats] this rank's data, double-buffered by the parity of the step
+    int* flags;                     // [RS_PEER_MAX] step counters written by the peers, [RS_PEER_MAX] = error latch
+    float* peer_buf[RS_PEER_MAX];   // the same buffers of every rank (own pointer for the own rank)
+    int* peer_flags[RS_PEER_MAX];
+    bool opened[RS_PEER_MAX];
+};
+struct PeerArgs { const float* buf[RS_PEER_MAX]; int* flags[RS_PEER_MAX]; int* my_flags; int rank, world; int step; long long n, off; };
+
+__global__ void __launch_bounds__(256) k_peer_allreduce(PeerArgs a, float* __restrict__ out) {
+    // (1) this rank's data is complete (the kernels that wrote it precede this one on the stream): tell every peer
+    if (blockIdx.x == 0 && threadIdx.x < a.world) {
+        __threadfence_system();
+        *((volatile int*)(a.flags[threadIdx.x] + a.rank)) = a.step;
+    }
+    // (2) wait for every peer's data of this step (the counters are monotonic, so a peer that is already a step ahead passes too)
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        const volatile int* f = (const volatile int*)(a.my_flags + threadIdx.x);
+        const long long t0 = clock64();
+        while (*f < a.step) {
+            __nanosleep(64);
+            if (clock64() - t0 > (1ll << 32)) { ok = 0; atomicExch(a.my_flags + RS_PEER_MAX, a.step); break; }      // ~2 s: give up, latch
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (!ok) return;
+    // (3) sum over the ranks in rank order; peer memory is read around the caches (it changes under this GPU's feet)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) {
+        float acc = 0.f;
+        for (int r = 0; r < a.world; r++) acc += __ldcv(a.buf[r] + a.off + i);
+        out[i] = acc;
+    }
+}
+
+extern "C" {
+int rs_peer_handle_bytes(void) { return 2 * (int)sizeof(cudaIpcMemHandle_t); }
+int rs_peer_create(int rank, int world, long long nfloats, int device, rs_peer** out) {
+    if (!out || world < 1 || world > RS_PEER_MAX || rank < 0 || rank >= world || nfloats <= 0) return fail(RS_ERR_ARG, "rs_peer_create: bad argument%s", "");
+    CUDA_OK(cudaSetDevice(device));
+    rs_peer* p = new rs_peer();
+    memset(p, 0, sizeof(*p));
+    p->rank = rank; p->world = world; p->device = device; p->nfloats = nfloats; p->step = 0;
+    CUDA_OK(cudaMalloc(&p->buf, sizeof(float) * 2 * nfloats)); CUDA_OK(cudaMemset(p->buf, 0, sizeof(float) * 2 * nfloats));
+    CUDA_OK(cudaMalloc(&p->flags, sizeof(int) * (RS_PEER_MAX + 1))); CUDA_OK(cudaMemset(p->flags, 0, sizeof(int) * (RS_PEER_MAX + 1)));
+    p->peer_buf[rank] = p->buf; p->peer_flags[rank] = p->flags;
+    *out = p;
+    return RS_OK;
+}
+int rs_peer_export(rs_peer* p, void* handle_out) {
+    if (!p || !handle_out) return fail(RS_ERR_ARG, "rs_peer_export: bad argument%s", "");
+    cudaIpcMemHandle_t h[2];
+    CUDA_OK(cudaIpcGetMemHandle(&h[0], p->buf)); CUDA_OK(cudaIpcGetMemHandle(&h[1], p->flags));
+    memcpy(handle_out, h, sizeof(h));
+    return RS_OK;
+}
+int rs_peer_connect(rs_peer* p, const void* all_handles) {
+    if (!p || !all_handles) return fail(RS_ERR_ARG, "rs_peer_connect: bad argument%s", "");
+    CUDA_OK(cudaSetDevice(p->device));
+    for (int r = 0; r < p->world; r++) {
+        if (r == p->rank) continue;
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, (const char*)all_handles + (size_t)r * sizeof(h), sizeof(h));
+        CUDA_OK(cudaIpcOpenMemHandle((void**)&p->peer_buf[r], h[0], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_OK(cudaIpcOpenMemHandle((void**)&p->peer_flags[r], h[1], cudaIpcMemLazyEnablePeerAccess));
+        p->opened[r] = true;
+    }
+    return RS_OK;
+}
+float* rs_peer_send_buffer(rs_peer* p) { return p ? p->buf + ((p->step + 1) & 1) * p->nfloats : nullptr; }
+int rs_peer_allreduce(rs_peer* p, float* out, long long nfloats, void* stream) {
+    if (!p || !out || nfloats <= 0 || nfloats > p->nfloats) return fail(RS_ERR_ARG, "rs_peer_allreduce: bad argument%s", "");
+    p->step++;
+    PeerArgs a;
+    for (int r = 0; r < p->world; r++) { a.buf[r] = p->peer_buf[r]; a.flags[r] = p->peer_flags[r]; }
+    a.my_flags = p->flags; a.rank = p->rank; a.world = p->world; a.step = (int)p->step; a.n = nfloats; a.off = (p->step & 1) * p->nfloats;
+    k_peer_allreduce<<<(unsigned)((nfloats + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, out);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return RS_OK;
+}
+int rs_peer_error(rs_peer* p) {
+    if (!p) return 0;
+    int e = 0;
+    if (cudaMemcpy(&e, p->flags + RS_PEER_MAX, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e;
+}
+void rs_peer_destroy(rs_peer* p) {
+    if (!p) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < p->world; r++) if (p->opened[r]) { cudaIpcCloseMemHandle(p->peer_buf[r]); cudaIpcCloseMemHandle(p->peer_flags[r]); }
+    cudaFree(p->buf); cudaFree(p->flags);
+    delete p;
+}
+}  // extern "C" (peer)
+
+extern "C" {
 /* data-parallel minibatch schedule: local index lists of every minibatch of an epoch from the global permutation (device) */
 int rs_epoch_split(const int* perm, long long n_global, int nbatch_train, long long lo, long long hi, int* out_idx, int* counts, void* stream) {
     if (!perm || !out_idx || !counts || n_global <= 0 || nbatch_train <= 0 || hi < lo) return fail(RS_ERR_ARG, "rs_epoch_split: bad argument%s", "");

@@ -59,6 +59,31 @@ class Comm:
         self.dist.broadcast(x, src=src)
         return int(x.item())
 
+    def make_peer(self, nfloats, device_index):
+        """An rs_peer handle for the gradient all-reduce over NVLink peer memory (include/rs_b200.h), or None when this job cannot
+        use it (one rank, CPU / gloo, ranks on several nodes, RS_B200_PEER=0): the caller then falls back to all_reduce_sum (NCCL).
+        Collective: every rank must call it at the same point."""
+        t = self.torch
+        if self.world == 1 or not t.cuda.is_available() or self.dist.get_backend() != 'nccl' or os.environ.get('RS_B200_PEER', '1') == '0':
+            return None
+        if int(os.environ.get('LOCAL_WORLD_SIZE', str(self.world))) != self.world:
+            return None                                   # CUDA IPC handles do not cross nodes
+        import ctypes
+        from . import _lib
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(L.rs_peer_create(self.rank, self.world, int(nfloats), int(device_index), ctypes.byref(h)))
+        nb = L.rs_peer_handle_bytes()
+        mine = (ctypes.c_ubyte * nb)()
+        _lib.check(L.rs_peer_export(h, mine))
+        dev = t.device('cuda', device_index)
+        gathered = t.empty(self.world * nb, dtype=t.uint8, device=dev)
+        self.dist.all_gather_into_tensor(gathered, t.tensor(list(mine), dtype=t.uint8, device=dev))
+        table = gathered.cpu().numpy().tobytes()
+        _lib.check(L.rs_peer_connect(h, table))
+        self.barrier()                                    # nobody signals a peer that has not mapped the buffers yet
+        return h
+
     def shard(self, n_global):
         """Contiguous env range of this rank: [lo, hi)."""
         per = n_global // self.world

@@ -32,6 +32,7 @@ class PPOModel:
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), max_grad_norm
         self.trainable = trainable
         self.comm = comm                        # robosumo_selfplay_b200.dist.Comm or None
+        self._peer_h = False                    # rs_peer handle of the gradient all-reduce: False = not set up yet, None = not available
         self._L = _lib.lib()
         assert self._L.rs_param_count(ob_dim, ac_dim) == self.P
         self.params = torch.as_tensor(init_params(ob_dim, ac_dim), device=self.device)       # consumes np.random like ortho_init
@@ -103,15 +104,34 @@ class PPOModel:
             _lib.check(L.rs_adv_moments(self._p(idx), n, self._p(returns), self._p(values), self._p(sums), st))
             if self.comm is not None:
                 self.comm.all_reduce_sum(sums)
+        peer = self._peer()
+        local = ctypes.c_void_p(L.rs_peer_send_buffer(peer)) if peer is not None else self._p(self.grad_stats)
         _lib.check(L.rs_ppo_grad(self._p(self.params), self.D, self.A, self._p(obs), self._p(actions), self._p(returns), self._p(values),
                                  self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(sums), float(cliprange),
-                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio),
+                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), local, self._p(log_ratio),
                                  self._p(stats), prec, st))
-        if self.comm is not None:
-            self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums]: THE collective of a minibatch step (98 KB, latency-bound)
+        # flat [grads | 4 stat sums]: THE collective of a minibatch step (98 KB, latency-bound).  One kernel of ours over NVLink peer
+        # memory on this stream when the ranks share a node (rs_peer_allreduce), else torch.distributed / NCCL.
+        if peer is not None:
+            _lib.check(L.rs_peer_allreduce(peer, self._p(self.grad_stats), self.P + 4, st))
+        elif self.comm is not None:
+            self.comm.all_reduce_sum(self.grad_stats)
         _lib.check(L.rs_adam_step(self._p(self.params), self._p(self.m), self._p(self.v), self._p(self.grad_stats), self.D, self.A,
                                   self.ent_coef, mgn, float(lr), self.t, 0.9, 0.999, 1e-5, self._p(self.gnorm), gn, self._p(stats), st))
         return stats, log_ratio
+
+    def _peer(self):
+        """The peer all-reduce handle of this model (created on first use: a collective, so every rank gets here together)."""
+        if self.comm is None or self.comm.world == 1:
+            return None
+        if self._peer_h is False:
+            self._peer_h = self.comm.make_peer(self.P + 4, self.device.index if self.device.index is not None else 0)
+        return self._peer_h
+
+    def check_peer(self):
+        """Raises if a peer all-reduce of this model ever timed out waiting for a rank (synchronises the device)."""
+        if self._peer_h not in (None, False) and self._L.rs_peer_error(self._peer_h) != 0:
+            raise RuntimeError("rs_peer_allreduce: a rank did not deliver its gradient within the time-out; parameters are no longer in sync")
 
     def stats_to_list(self, stats_dev):
         return [float(x) for x in stats_dev.double().cpu().numpy()]

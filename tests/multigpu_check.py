@@ -60,13 +60,25 @@ if __name__ == '__main__':
         sizes[-1] += N - sum(sizes)
         lo = sum(sizes[:comm.rank]); hi = lo + sizes[comm.rank]
         p_multi, counts = train(m, dd, lo, hi, comm)
+        m.check_peer()
+        peer_used = m._peer_h not in (None, False)
+        # the same training with the gradient all-reduce through torch.distributed / NCCL instead of the peer-memory kernel
+        np.random.seed(3)
+        os.environ['RS_B200_PEER'] = '0'
+        m2 = PPOModel(ob_dim=D, ac_dim=A, device=comm.local_rank, comm=comm, precision=precision)
+        p_nccl, _ = train(m2, dd, lo, hi, comm)
+        os.environ['RS_B200_PEER'] = '1'
+        assert m2._peer_h is None
         tot = torch.tensor(counts, dtype=torch.int64, device=dev)
         comm.all_reduce_sum(tot)
         ok &= bool((tot == N // NMB).all())                                   # every global minibatch is partitioned exactly
         d = np.abs(p_single - p_multi)
         moved = float(np.abs(p_single - init).max())
+        dn = np.abs(p_nccl - p_multi)
         out[precision] = dict(max_abs_diff=float(d.max()), moved=moved, worst_index=int(d.argmax()),
-                              n_above_1e_6=int((d > 1e-6).sum()), median_abs_diff=float(np.median(d)), n_params=int(d.size))
+                              n_above_1e_6=int((d > 1e-6).sum()), median_abs_diff=float(np.median(d)), n_params=int(d.size),
+                              peer_allreduce=bool(peer_used), peer_vs_nccl_max_abs_diff=float(dn.max()))
+        ok &= dn.max() <= (2e-6 if precision == 'fp32' else 0.03 * moved)      # rank-order sums (peer kernel) vs NCCL's order
         # fp32 pipe: summation-order differences only; tf32: the tensor core's grouping-dependent accumulation, amplified by Adam
         ok &= d.max() <= (2e-6 if precision == 'fp32' else 0.03 * moved)
     # learn() data-parallel with opponent_mode='ours' and opponent-data reuse: identical opponent choices and parameters on every rank
