@@ -223,11 +223,12 @@ def measure_learner(args, E, local, rank, world, dev):
     lo, hi = rank * N_local, (rank + 1) * N_local
     model = models[0]
     sched = EpochSchedule(dev, N, nbt, lo, hi, comm)
+    split = (nbt, lo, hi) if comm is not None else None      # data-parallel: the helper thread hands out this rank's cut of the permutation (dist.host_split)
     l0 = _lib.lib().rs_launch_count()
     def one_update(perms=None):
         # the reference's per-epoch np.random.shuffle, replayed bit-exactly on the host (one epoch ahead on a helper thread); the
         # permutation goes to the device once per epoch, where the minibatches are split by rank and their advantage moments computed
-        for inds in (perms if perms is not None else EpochPermutations(N, nep, dtype=np.int32)):
+        for inds in (perms if perms is not None else EpochPermutations(N, nep, dtype=np.int32, split=split)):
             for mb, n_loc, gn, sums in sched.load(inds, data['returns'], data['values']):
                 model.train_indexed(1e-3, 0.2, data['obs'], data['returns'], data['actions'], data['values'], data['neglogpacs'], None, mb,
                                     global_n=gn, adv_sums=sums)
@@ -242,7 +243,7 @@ def measure_learner(args, E, local, rank, world, dev):
     upd_s = time.perf_counter() - t0
     # the same update the way alg_ppo.learn runs it: the six permutations depend on the generator stream only and are drawn on the
     # helper thread WHILE the rollout runs, so inside the training loop the update does not wait for them
-    perms = EpochPermutations(N, nep, ahead=nep, dtype=np.int32)
+    perms = EpochPermutations(N, nep, ahead=nep, dtype=np.int32, split=split)
     runner.run(1, as_numpy=False)
     torch.cuda.synchronize()
     if comm is not None:

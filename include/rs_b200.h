@@ -154,6 +154,8 @@ int rs_adam_step(float* params, float* m, float* v, float* grad, int obs_dim, in
  * (int32, device; every rank holds the same one) the LOCAL indices of every minibatch that fall in this rank's sample range
  * [lo, hi): out_idx [nmb][nbatch_train] (minibatch m at out_idx + m * nbatch_train, order preserved), counts [nmb] */
 int rs_epoch_split(const int* perm, long long n_global, int nbatch_train, long long lo, long long hi, int* out_idx, int* counts, void* stream);
+/* the same cut on the HOST (no GPU involved), for the helper thread that draws the permutation: `local` needs hi - lo + 1 slots */
+int rs_epoch_split_host(const void* perm, int elem_bytes /* 4 or 8 */, long long n_global, int nbatch_train, long long lo, long long hi, int* local, int* counts);
 /* advantage moments (model.py:182-185) of ALL minibatches of an epoch in one launch: sums [nmb][2] doubles; idx [nmb][cap] (NULL =
  * identity over n_total samples), counts [nmb] (NULL = full slices).  Returns and values are constant during an update, so a
  * data-parallel caller all-reduces these once per epoch instead of once per minibatch */
@@ -197,6 +199,14 @@ int rs_peer_allreduce(rs_peer* p, float* out, long long nfloats, void* stream);
 int rs_peer_error(rs_peer* p);                                     /* non-zero after a timed-out wait (synchronises the device) */
 void rs_peer_destroy(rs_peer* p);
 
+/* data-parallel minibatch step in ONE call: rs_ppo_grad (into the peer buffer) -> rs_peer_allreduce -> rs_adam_step, 4 launches and no
+ * host work in between, so that the host stays ahead of the GPU (with three separate calls the Python side of a minibatch took as
+ * long as its kernels and every hiccup of one of N ranks stalled all of them).  adv_sums: GLOBAL moments of the minibatch. */
+int rs_ppo_minibatch_step_peer(rs_peer* peer, float* params, float* m, float* v, int obs_dim, int act_dim, const float* obs, const float* actions,
+                               const float* returns, const float* values, const float* old_nlp, const float* weights, const int* idx, int n,
+                               long long global_n, float cliprange, float ent_coef, float vf_coef, float max_grad_norm, float lr, long long step_t,
+                               float* workspace, float* grad_stats, const double* adv_sums, float* gnorm_out, double* stats5, float* log_ratio,
+                               int precision, void* stream);
 /* single-GPU convenience: [rs_adv_moments ->] rs_ppo_grad -> rs_adam_step in ONE call, 3 launches (a data-parallel caller uses the
  * pieces and all-reduces grad_stats between them).  beta1 = 0.9, beta2 = 0.999, eps = 1e-5 as model.py:121; adv_sums [2] doubles
  * (already filled when moments_ready != 0, e.g. by rs_adv_moments_multi) and grad_stats [P + 8] floats are caller-owned device buffers. */
@@ -212,6 +222,8 @@ int rs_ppo_minibatch_step(float* params, float* m, float* v, int obs_dim, int ac
  * Algorithm restated from NumPy's legacy generator (RandomState.shuffle -> _shuffle_raw: for i = n-1 .. 1: j = interval(i); swap;
  * interval = masked rejection sampling on 32-bit MT19937 outputs while i <= 0xffffffff). */
 int rs_legacy_shuffle(uint32_t* key, int* pos, int64_t* x, long long n);
+/* the same permutation and generator state on an int32 array (n < 2^31): half the bytes under the random accesses */
+int rs_legacy_shuffle32(unsigned int* key, int* pos, int* x, long long n);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long rs_launch_count(void);

@@ -63,11 +63,15 @@ SYMBOLS = {
     'rs_ppo_minibatch_step': (c_int, [c_void_p] * 3 + [c_int, c_int] + [c_void_p] * 7 + [c_int, c_float, c_float, c_float, c_float, c_float,
                                       ctypes.c_longlong] + [c_void_p] * 3 + [c_int] + [c_void_p] * 3 + [c_int, c_void_p]),
     'rs_epoch_split': (c_int, [c_void_p, ctypes.c_longlong, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
+    'rs_epoch_split_host': (c_int, [c_void_p, c_int, ctypes.c_longlong, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]),
     'rs_adv_moments_multi': (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
     'rs_status_latch': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'rs_seed': (c_int, [c_void_p, ctypes.c_ulonglong]),
     'rs_legacy_shuffle': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong]),
+    'rs_legacy_shuffle32': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong]),
     'rs_ppo_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
+    'rs_ppo_minibatch_step_peer': (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 7 + [c_int, ctypes.c_longlong, c_float, c_float, c_float, c_float, c_float,
+                                           ctypes.c_longlong] + [c_void_p] * 6 + [c_int, c_void_p]),
     'rs_peer_create': (c_int, [c_int, c_int, ctypes.c_longlong, c_int, ctypes.POINTER(c_void_p)]),
     'rs_peer_handle_bytes': (c_int, []),
     'rs_peer_export': (c_int, [c_void_p, c_void_p]),

@@ -339,7 +339,8 @@ def learn(*, network='mlp', env, total_timesteps, eval_env=None, opponent_mode='
 
         # the update's permutations depend on the generator stream only: when the sample count is known up front they are all
         # computed on a helper thread WHILE the rollout runs (nothing else draws from np.random until they are consumed)
-        perms = EpochPermutations(nbatch, noptepochs, ahead=noptepochs, dtype=np.int32) if use_opponent_data is None else None
+        split = (nbatch_train, rank * nbatch_local, (rank + 1) * nbatch_local) if world > 1 else None      # data-parallel: the helper thread also cuts out this rank's part
+        perms = EpochPermutations(nbatch, noptepochs, ahead=noptepochs, dtype=np.int32, split=split) if use_opponent_data is None else None
         # ---- rollout (device resident) ----
         R = runner.run(update, as_numpy=False)
         prev = R
@@ -369,7 +370,8 @@ def learn(*, network='mlp', env, total_timesteps, eval_env=None, opponent_mode='
 
         # ---- epochs x minibatches (alg_ppo.py:355-398) ----
         if perms is None:
-            perms = EpochPermutations(update_sample_num, noptepochs, dtype=np.int32)     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
+            perms = EpochPermutations(update_sample_num, noptepochs, dtype=np.int32,     # np.random.shuffle(inds) per epoch, replayed bit-exactly one epoch ahead (dist.py)
+                                      split=(nbatch_train, lo, hi) if world > 1 else None)
         assert perms._inds.shape[0] == update_sample_num
         if sched is None or sched.n_total != update_sample_num or sched.lo != lo or sched.hi != hi:
             sched = EpochSchedule(device, update_sample_num, nbatch_train, lo, hi, comm)

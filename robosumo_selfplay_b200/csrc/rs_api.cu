@@ -889,6 +889,24 @@ void rs_peer_destroy(rs_peer* p) {
 }  // extern "C" (peer)
 
 extern "C" {
+/* data-parallel minibatch step in ONE call (4 launches, no host work in between): local gradient into this rank's peer buffer ->
+ * rs_peer_allreduce -> clip + Adam + statistics.  adv_sums holds the GLOBAL advantage moments of the minibatch (dist.EpochSchedule). */
+int rs_ppo_minibatch_step_peer(rs_peer* peer, float* params, float* m, float* v, int obs_dim, int act_dim, const float* obs, const float* actions,
+                               const float* returns, const float* values, const float* old_nlp, const float* weights, const int* idx, int n,
+                               long long global_n, float cliprange, float ent_coef, float vf_coef, float max_grad_norm, float lr, long long step_t,
+                               float* workspace, float* grad_stats, const double* adv_sums, float* gnorm_out, double* stats5, float* log_ratio,
+                               int precision, void* stream) {
+    if (!peer) return fail(RS_ERR_ARG, "rs_ppo_minibatch_step_peer: null peer%s", "");
+    const rsl::Layout L = rsl::make_layout(obs_dim, act_dim);
+    int rc = rs_ppo_grad(params, obs_dim, act_dim, obs, actions, returns, values, old_nlp, weights, idx, n, global_n, adv_sums, cliprange, ent_coef,
+                         vf_coef, workspace, rs_peer_send_buffer(peer), log_ratio, stats5, precision, stream);
+    if (rc) return rc;
+    rc = rs_peer_allreduce(peer, grad_stats, L.P + 4, stream);
+    if (rc) return rc;
+    return rs_adam_step(params, m, v, grad_stats, obs_dim, act_dim, ent_coef, max_grad_norm, lr, step_t, 0.9f, 0.999f, 1e-5f, gnorm_out, global_n, stats5, stream);
+}
+}  // extern "C"
+extern "C" {
 /* data-parallel minibatch schedule: local index lists of every minibatch of an epoch from the global permutation (device) */
 int rs_epoch_split(const int* perm, long long n_global, int nbatch_train, long long lo, long long hi, int* out_idx, int* counts, void* stream) {
     if (!perm || !out_idx || !counts || n_global <= 0 || nbatch_train <= 0 || hi < lo) return fail(RS_ERR_ARG, "rs_epoch_split: bad argument%s", "");
@@ -906,6 +924,36 @@ int rs_adv_moments_multi(const int* idx, const int* counts, int nmb, int cap, lo
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return RS_OK;
+}
+
+/* host-side data-parallel cut of a global permutation (int64, as np.random.shuffle leaves it): the entries inside [lo, hi) as local
+ * int32 indices, in order, concatenated over the minibatches, and how many each minibatch of nbatch_train entries holds */
+}  // extern "C"
+template <typename T>
+static int epoch_split_host_core(const T* perm, long long n_global, int nbatch_train, long long lo, long long hi, int* local, int* counts) {
+    long long w = 0;
+    int m = 0;
+    const long long cap = hi - lo;
+    for (long long s0 = 0; s0 < n_global; s0 += nbatch_train, m++) {
+        const long long s1 = s0 + nbatch_train < n_global ? s0 + nbatch_train : n_global;
+        const long long w0 = w;
+        if (w + (s1 - s0) <= cap) {      // no overflow possible inside this minibatch: tight branch-free loop
+            for (long long i = s0; i < s1; i++) { const long long v = (long long)perm[i]; local[w] = (int)(v - lo); w += (v >= lo) & (v < hi); }
+        } else {
+            for (long long i = s0; i < s1; i++) {
+                const long long v = (long long)perm[i];
+                if (v >= lo && v < hi) { if (w >= cap) return fail(RS_ERR_ARG, "rs_epoch_split_host: not a permutation%s", ""); local[w++] = (int)(v - lo); }
+            }
+        }
+        counts[m] = (int)(w - w0);
+    }
+    return RS_OK;
+}
+extern "C" {
+int rs_epoch_split_host(const void* perm, int elem_bytes, long long n_global, int nbatch_train, long long lo, long long hi, int* local, int* counts) {
+    if (!perm || !local || !counts || n_global <= 0 || nbatch_train <= 0 || hi < lo || (elem_bytes != 4 && elem_bytes != 8)) return fail(RS_ERR_ARG, "rs_epoch_split_host: bad argument%s", "");
+    return elem_bytes == 4 ? epoch_split_host_core((const int32_t*)perm, n_global, nbatch_train, lo, hi, local, counts)
+                           : epoch_split_host_core((const int64_t*)perm, n_global, nbatch_train, lo, hi, local, counts);
 }
 
 // ---- legacy NumPy shuffle replay (host) -----------------------------------------------------------------------------------
@@ -932,7 +980,9 @@ struct MtStream {
         return out[pos++];
     }
 };
-int rs_legacy_shuffle(uint32_t* key, int* pos, int64_t* x, long long n) {
+}  // extern "C"
+template <typename T>
+static int legacy_shuffle_core(uint32_t* key, int* pos, T* x, long long n) {
     if (!key || !pos || !x || n < 0 || *pos < 0 || *pos > 624) return fail(RS_ERR_ARG, "rs_legacy_shuffle: bad argument%s", "");
     if (n > 0x100000000LL) return fail(RS_ERR_UNSUPPORTED, "rs_legacy_shuffle: n beyond the 32-bit interval path%s", "");
     MtStream g; g.key = key; g.pos = *pos;
@@ -953,10 +1003,17 @@ int rs_legacy_shuffle(uint32_t* key, int* pos, int64_t* x, long long n) {
             jj[q] = (long long)j;
             __builtin_prefetch(x + j, 1, 0);
         }
-        for (int q = 0; q < m; q++) { const long long a = i - q, b = jj[q]; const int64_t tmp = x[a]; x[a] = x[b]; x[b] = tmp; }
+        for (int q = 0; q < m; q++) { const long long a = i - q, b = jj[q]; const T tmp = x[a]; x[a] = x[b]; x[b] = tmp; }
     }
     *pos = g.pos;
     return RS_OK;
+}
+extern "C" {
+int rs_legacy_shuffle(uint32_t* key, int* pos, int64_t* x, long long n) { return legacy_shuffle_core<int64_t>(key, pos, x, n); }
+/* the same permutation on an int32 array (n < 2^31): half the bytes under the random accesses, which is what the routine waits for */
+int rs_legacy_shuffle32(uint32_t* key, int* pos, int32_t* x, long long n) {
+    if (n >= 0x7fffffffLL) return fail(RS_ERR_UNSUPPORTED, "rs_legacy_shuffle32: n does not fit int32%s", "");
+    return legacy_shuffle_core<int32_t>(key, pos, x, n);
 }
 
 /* tcgen05 descriptor/layout self-test: D[128,64] = op(A) * op(B) through kind::tf32 UMMA (see rs_tc.cuh) */

@@ -99,6 +99,37 @@ def split_minibatch(global_idx, lo, hi):
     return (g[m] - lo).astype(np.int32)
 
 
+class SplitPerm:
+    """One epoch's permutation already cut into this rank's minibatch parts on the host: idx [nmb][cap] local indices, counts [nmb]."""
+    __slots__ = ('idx', 'counts', 'n_total', 'cap')
+
+    def __init__(self, idx, counts, n_total):
+        self.idx, self.counts, self.n_total, self.cap = idx, counts, int(n_total), int(idx.shape[1])
+
+
+def host_split(perm, nbt, lo, hi):
+    """The data-parallel cut of a global permutation, on the host (safe on the helper thread of EpochPermutations):
+    per minibatch m the entries of perm[m*nbt:(m+1)*nbt] inside this rank's sample range [lo, hi), in order, as local indices
+    (one pass of the library's host routine rs_epoch_split_host, which releases the GIL).
+    With N ranks the global permutation has N x as many entries as a rank trains on; cutting it where it is drawn keeps the per-epoch
+    upload at the rank's own 4 bytes per sample instead of the whole permutation (8 GPUs: 2 MB instead of 16 MB per epoch and rank)."""
+    import ctypes
+    import numpy as np
+    from . import _lib
+    n = int(perm.shape[0]); nbt = int(nbt)
+    nmb = (n + nbt - 1) // nbt
+    pc = np.ascontiguousarray(perm) if perm.dtype in (np.int32, np.int64) else np.ascontiguousarray(perm, dtype=np.int64)
+    local = np.empty(int(hi - lo) + 1, np.int32); counts = np.empty(nmb, np.int32)
+    _lib.check(_lib.lib().rs_epoch_split_host(ctypes.c_void_p(pc.ctypes.data), pc.dtype.itemsize, ctypes.c_longlong(n), nbt, ctypes.c_longlong(int(lo)),
+                                             ctypes.c_longlong(int(hi)), ctypes.c_void_p(local.ctypes.data), ctypes.c_void_p(counts.ctypes.data)))
+    cap = max(int(counts.max()), 1)
+    idx = np.zeros((nmb, cap), np.int32)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    for m in range(nmb):
+        idx[m, :counts[m]] = local[off[m]:off[m + 1]]
+    return SplitPerm(idx, counts, n)
+
+
 class EpochSchedule:
     """The minibatch schedule of one epoch ON THE DEVICE (replaces the per-minibatch NumPy masks of round 1).
 
@@ -130,10 +161,13 @@ class EpochSchedule:
         return ctypes.c_void_p(x.data_ptr()) if x is not None else None
 
     def load(self, perm, returns, values):
-        """perm: the epoch's global permutation (numpy, any integer dtype).  Returns the list of minibatch parts."""
+        """perm: the epoch's global permutation (numpy, any integer dtype), or its host-side cut (SplitPerm, data-parallel).
+        Returns the list of minibatch parts."""
         import ctypes
         import numpy as np
         t = self.t
+        if isinstance(perm, SplitPerm):
+            return self._load_split(perm, returns, values)
         if self.copied is not None:
             self.copied.synchronize()                       # the previous upload has left the staging buffer
         np.copyto(self.stage.numpy(), perm, casting='unsafe')
@@ -152,6 +186,35 @@ class EpochSchedule:
         self.comm.all_reduce_sum(self.sums)                 # ONE collective per epoch for all advantage moments
         counts = self.counts.cpu().tolist()                 # one small D2H per epoch: the launch geometry of the local parts
         return [(self.idx[m * self.nbt:m * self.nbt + counts[m]], counts[m], sizes[m], self.sums[m]) for m in range(self.nmb)]
+
+
+    def _load_split(self, sp, returns, values):
+        """Data-parallel with the cut already made on the host: ONE upload of [counts | idx] (this rank's 4 bytes per sample), the
+        advantage moments of all minibatches in one launch, one all-reduce of them per epoch; no device-to-host copy."""
+        import ctypes
+        t = self.t
+        assert sp.n_total == self.n_total and sp.idx.shape[0] == self.nmb
+        need = self.nmb + self.nmb * sp.cap
+        if getattr(self, '_sbuf', None) is None or self._sbuf.numel() < need:
+            self._sbuf = t.empty(need + need // 8, dtype=t.int32, device=self.device)
+            self._sstage = t.empty(need + need // 8, dtype=t.int32, pin_memory=t.cuda.is_available())
+        if self.copied is not None:
+            self.copied.synchronize()
+        h = self._sstage.numpy()
+        h[:self.nmb] = sp.counts
+        h[self.nmb:need] = sp.idx.ravel()
+        self._sbuf[:need].copy_(self._sstage[:need], non_blocking=True)
+        if t.cuda.is_available():
+            self.copied = t.cuda.Event(); self.copied.record(t.cuda.current_stream(self.device))
+        st = ctypes.c_void_p(t.cuda.current_stream(self.device).cuda_stream)
+        counts_dev, idx_dev = self._sbuf[:self.nmb], self._sbuf[self.nmb:need]
+        self._lib.check(self.L.rs_adv_moments_multi(self._p(idx_dev), self._p(counts_dev), self.nmb, sp.cap, self.n_total, self._p(returns),
+                                                    self._p(values), self._p(self.sums), st))
+        if self.comm is not None:
+            self.comm.all_reduce_sum(self.sums)
+        sizes = [min(self.nbt, self.n_total - m * self.nbt) for m in range(self.nmb)]
+        counts = [int(c) for c in sp.counts]
+        return [(idx_dev[m * sp.cap:m * sp.cap + counts[m]], counts[m], sizes[m], self.sums[m]) for m in range(self.nmb)]
 
 
 def legacy_shuffle(inds):
@@ -181,8 +244,9 @@ class EpochPermutations:
     so an early stop (kl_threshold) leaves the stream exactly where the reference would: nothing speculative is committed.
     Nobody else may draw from `np.random` between construction and the last `next()` (the rollout and the update do not)."""
 
-    def __init__(self, n, nepochs, ahead=1, dtype=None):
+    def __init__(self, n, nepochs, ahead=1, dtype=None, split=None):
         import numpy as np
+        self._split = split                 # (nbatch_train, lo, hi): data-parallel, hand out the host-side cut of this rank (SplitPerm) instead of the permutation
         self._dtype = dtype                 # e.g. np.int32: the helper thread hands out the permutation already narrowed for the device upload
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
@@ -190,9 +254,10 @@ class EpochPermutations:
         assert name == 'MT19937'
         self._key = np.ascontiguousarray(key, dtype=np.uint32).copy()
         self._pos = int(pos)
-        self._inds = np.arange(n)
+        self._inds = np.arange(n, dtype=np.int32 if n < 2**31 - 1 else np.int64)      # int32: half the bytes under the shuffle's random accesses
         self._left = int(nepochs)
         self._pool = ThreadPoolExecutor(max_workers=1)       # one worker: the shuffles continue one generator stream, in order
+        self._pool2 = ThreadPoolExecutor(max_workers=1) if split is not None else None      # the cut of epoch k runs beside the shuffle of epoch k + 1
         self._queue = deque()
         for _ in range(max(1, int(ahead))):
             self._launch()
@@ -201,15 +266,23 @@ class EpochPermutations:
         import ctypes
         from . import _lib
         p = ctypes.c_int(self._pos)
-        _lib.check(_lib.lib().rs_legacy_shuffle(ctypes.c_void_p(self._key.ctypes.data), ctypes.byref(p),
-                                                ctypes.c_void_p(self._inds.ctypes.data), ctypes.c_longlong(self._inds.shape[0])))
+        fn = _lib.lib().rs_legacy_shuffle32 if self._inds.dtype.itemsize == 4 else _lib.lib().rs_legacy_shuffle
+        _lib.check(fn(ctypes.c_void_p(self._key.ctypes.data), ctypes.byref(p), ctypes.c_void_p(self._inds.ctypes.data), ctypes.c_longlong(self._inds.shape[0])))
         self._pos = p.value
-        return (self._inds.copy() if self._dtype is None else self._inds.astype(self._dtype)), self._key.copy(), self._pos
+        if self._split is not None:
+            return self._inds.copy(), self._key.copy(), self._pos
+        import numpy as np
+        return self._inds.astype(self._dtype if self._dtype is not None else np.int64), self._key.copy(), self._pos
+
+    def _cut(self, fut):
+        perm, key, pos = fut.result()
+        return host_split(perm, *self._split), key, pos
 
     def _launch(self):
         if self._left > 0:
             self._left -= 1
-            self._queue.append(self._pool.submit(self._compute))
+            f = self._pool.submit(self._compute)
+            self._queue.append(self._pool2.submit(self._cut, f) if self._pool2 is not None else f)
 
     def __iter__(self):
         return self
@@ -218,6 +291,8 @@ class EpochPermutations:
         import numpy as np
         if not self._queue:
             self._pool.shutdown(wait=False)
+            if self._pool2 is not None:
+                self._pool2.shutdown(wait=False)
             raise StopIteration
         perm, key, pos = self._queue.popleft().result()
         np.random.set_state(('MT19937', key, pos, self._hg, self._cg))
@@ -229,3 +304,5 @@ class EpochPermutations:
         while self._queue:
             self._queue.popleft().result()
         self._pool.shutdown(wait=False)
+        if self._pool2 is not None:
+            self._pool2.shutdown(wait=False)

@@ -105,17 +105,20 @@ class PPOModel:
             if self.comm is not None:
                 self.comm.all_reduce_sum(sums)
         peer = self._peer()
-        local = ctypes.c_void_p(L.rs_peer_send_buffer(peer)) if peer is not None else self._p(self.grad_stats)
+        if peer is not None:                        # data-parallel on one node: the whole step is one library call (gradient all-reduce = rs_peer_allreduce,
+                                                    # ONE kernel of ours over NVLink peer memory on this stream)
+            _lib.check(L.rs_ppo_minibatch_step_peer(peer, self._p(self.params), self._p(self.m), self._p(self.v), self.D, self.A, self._p(obs),
+                                                    self._p(actions), self._p(returns), self._p(values), self._p(neglogpacs), self._p(weights),
+                                                    self._p(idx), n, gn, float(cliprange), self.ent_coef, self.vf_coef, mgn, float(lr), self.t,
+                                                    self._p(self._workspace(n)), self._p(self.grad_stats), self._p(sums), self._p(self.gnorm),
+                                                    self._p(stats), self._p(log_ratio), prec, st))
+            return stats, log_ratio
         _lib.check(L.rs_ppo_grad(self._p(self.params), self.D, self.A, self._p(obs), self._p(actions), self._p(returns), self._p(values),
                                  self._p(neglogpacs), self._p(weights), self._p(idx), n, gn, self._p(sums), float(cliprange),
-                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), local, self._p(log_ratio),
+                                 self.ent_coef, self.vf_coef, self._p(self._workspace(n)), self._p(self.grad_stats), self._p(log_ratio),
                                  self._p(stats), prec, st))
-        # flat [grads | 4 stat sums]: THE collective of a minibatch step (98 KB, latency-bound).  One kernel of ours over NVLink peer
-        # memory on this stream when the ranks share a node (rs_peer_allreduce), else torch.distributed / NCCL.
-        if peer is not None:
-            _lib.check(L.rs_peer_allreduce(peer, self._p(self.grad_stats), self.P + 4, st))
-        elif self.comm is not None:
-            self.comm.all_reduce_sum(self.grad_stats)
+        if self.comm is not None:                   # ranks on several nodes / gloo / RS_B200_PEER=0: torch.distributed (NCCL) all-reduce of the
+            self.comm.all_reduce_sum(self.grad_stats)          # flat [grads | 4 stat sums] (98 KB, latency-bound)
         _lib.check(L.rs_adam_step(self._p(self.params), self._p(self.m), self._p(self.v), self._p(self.grad_stats), self.D, self.A,
                                   self.ent_coef, mgn, float(lr), self.t, 0.9, 0.999, 1e-5, self._p(self.gnorm), gn, self._p(stats), st))
         return stats, log_ratio

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
-from robosumo_selfplay_b200.dist import Comm, EpochSchedule   # noqa: E402
+from robosumo_selfplay_b200.dist import Comm, EpochSchedule, host_split   # noqa: E402
 from robosumo_selfplay_b200.model import PPOModel             # noqa: E402
 
 D, A, N, NMB, STEPS = 121, 8, 8192, 4, 3
@@ -36,7 +36,9 @@ def train(model, dd, lo, hi, comm):
     counts = []
     for _ in range(STEPS):
         rng.shuffle(inds)
-        for idx, n_loc, gn, sums in sched.load(inds, t['ret'], t['val']):
+        # data-parallel: alternate between the device-side cut of the permutation (rs_epoch_split) and the host-side one (host_split)
+        perm = host_split(inds, N // NMB, lo, hi) if (comm is not None and _ % 2 == 1) else inds
+        for idx, n_loc, gn, sums in sched.load(perm, t['ret'], t['val']):
             counts.append(n_loc)
             model.train_indexed(1e-3, 0.2, t['obs'], t['ret'], t['act'], t['val'], t['old'], None, idx, global_n=gn, adv_sums=sums)
     return model.get_flat(), counts

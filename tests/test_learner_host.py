@@ -66,6 +66,26 @@ def test_minibatch_split_partitions_global_indices():
         assert sorted(np.concatenate(parts).tolist()) == sorted(mb.tolist())
 
 
+def test_host_split_equals_the_per_minibatch_masks():
+    """dist.host_split (the data-parallel cut made on the helper thread) against the reference-style masks of split_minibatch:
+    same local indices in the same order for every minibatch, ragged last minibatch and ragged rank ranges included."""
+    from robosumo_selfplay_b200.dist import host_split, split_minibatch
+    rng = np.random.RandomState(3)
+    N, nbt = 5000, 384                          # 13 full minibatches + one of 8
+    perm = rng.permutation(N).astype(np.int32)
+    bounds = [0, 1237, 2500, 2501, N]           # unequal ranges, one of a single sample
+    total = np.zeros(14, np.int64)
+    for r in range(4):
+        lo, hi = bounds[r], bounds[r + 1]
+        sp = host_split(perm, nbt, lo, hi)
+        assert sp.idx.shape[0] == 14 and sp.n_total == N and sp.idx.dtype == np.int32
+        for m in range(14):
+            want = split_minibatch(perm[m * nbt:(m + 1) * nbt], lo, hi)
+            assert sp.counts[m] == len(want) and np.array_equal(sp.idx[m, :sp.counts[m]], want)
+        total += sp.counts
+    assert total.tolist() == [nbt] * 13 + [8]
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), LOCAL_RANK=str(rank))
     import torch
