@@ -187,7 +187,7 @@ int rs_get_diag(rs_env* h, int* diag, void* stream);
  * double-buffered symmetric buffer that its peers map through CUDA IPC; rs_ppo_grad writes the local gradient into
  * rs_peer_send_buffer(), rs_peer_allreduce then (1) raises this rank's step counter in every peer's flag array, (2) waits for the
  * peers' counters and (3) sums the `nfloats` entries over the ranks in rank order (bit-identical on every rank) into `out`.
- * No host synchronisation and no second stream; a peer that never arrives makes the kernel give up after ~2 s and latches an
+ * No host synchronisation and no second stream; a peer that never arrives makes the kernel give up after ~9 s and latches an
  * error that rs_peer_error() reports.  Handles are exchanged by the caller (dist.py: one all_gather of rs_peer_handle_bytes()). */
 typedef struct rs_peer rs_peer;
 int rs_peer_create(int rank, int world, long long nfloats, int device, rs_peer** out);

@@ -810,9 +810,10 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerArgs a, float* __res
     if (threadIdx.x < a.world) {
         const volatile int* f = (const volatile int*)(a.my_flags + threadIdx.x);
         const long long t0 = clock64();
-        while (*f < a.step) {
+        if (*((const volatile int*)(a.my_flags + RS_PEER_MAX)) != 0) ok = 0;      // an earlier wait already failed: the replicas are out of step, do not spin again
+        else while (*f < a.step) {
             __nanosleep(64);
-            if (clock64() - t0 > (1ll << 32)) { ok = 0; atomicExch(a.my_flags + RS_PEER_MAX, a.step); break; }      // ~2 s: give up, latch
+            if (clock64() - t0 > (1ll << 34)) { ok = 0; atomicExch(a.my_flags + RS_PEER_MAX, a.step); break; }      // ~9 s: give up, latch
         }
     }
     __syncthreads();

@@ -16,7 +16,13 @@
 //    direction Jacobians;
 //  * the soft-constraint problem is solved in the primal (Newton with exact line search on
 //    the one-sided quadratic rows of the pyramidal cone), which is the reference's configured
-//    solver, warm-started from the previous stage.
+//    solver, warm-started from the previous stage; the Newton system keeps M's arrowhead form
+//    (arrow_solve) and contacts between the two agents enter as a low-rank correction of it
+//    (woodbury_solve);
+//  * the warps of a block re-align once per "trip" (evaluation start + one Newton iteration,
+//    simulate_trips) so that they share the instruction stream without waiting for each
+//    other's extra iterations; with more pairs than warp slots the blocks are persistent and
+//    a warp takes its next pair off a device counter (rs_api.cu).
 //
 // Code is written as phases of independent "items" (RS_LANE_LOOP) separated by warp syncs
 // and communicating only through the slab, so that the same source also compiles as a
