@@ -166,3 +166,34 @@ def test_ragged_batch_sizes(E):
         ob, rb, db, _ = big.step(a)
         o, r, d, _ = env.step(a[:E].contiguous())
         assert torch.isfinite(o).all() and torch.equal(o, ob[:E]) and torch.equal(r, rb[:E]) and torch.equal(d, db[:E])
+
+
+def test_persistent_blocks_equal_one_pair_per_warp():
+    """More pairs than warp slots (E > SMs x 28): k_step runs persistent blocks whose warps take pairs off a device counter, in
+    whatever order they get free.  A pair's result must not depend on that: the same states stepped 28 x 148 at a time (one pair per
+    warp, no counter) give bit-identical observations, rewards and flags, three steps in a row (the counter alternates)."""
+    import torch
+    from robosumo_selfplay_b200.vec_env import B200SumoVecEnv
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    chunk = 28 * sms
+    E = 2 * chunk + 1234                                  # 2.3 waves
+    big = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=E, seed=5, device_api=True, auto_reset=True)
+    big.reset()
+    q, v, _, _ = big.get_state()
+    parts = []
+    for lo in range(0, E, chunk):
+        n = min(chunk, E - lo)
+        e = B200SumoVecEnv('RoboSumo-Ant-vs-Ant-v0', num_envs=n, seed=5, device_api=True, auto_reset=False)
+        e.reset(); e.set_state(q[lo:lo + n], v[lo:lo + n])
+        parts.append((lo, n, e))
+    big.set_state(q, v)
+    g = torch.Generator(device='cuda'); g.manual_seed(9)
+    for t in range(3):
+        a = torch.randn(E, 2, 8, device='cuda', generator=g)
+        ob, rb, db, _ = big.step(a)
+        keep = ~db[:, 0].bool()                           # (pairs that ended were auto-reset in `big` only: compare the others' observations)
+        for lo, n, e in parts:
+            o, r, d, _ = e.step(a[lo:lo + n].contiguous())
+            k = keep[lo:lo + n]
+            assert torch.equal(r, rb[lo:lo + n]) and torch.equal(d, db[lo:lo + n]) and torch.equal(o[k], ob[lo:lo + n][k])
+    assert int(keep.sum()) > E // 2
