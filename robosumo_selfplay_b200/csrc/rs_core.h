@@ -46,10 +46,26 @@
 #define RS_ATOMIC_INC(p) atomicAdd((p), 1)
 #define RS_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define RS_LANE0 ((threadIdx.x & 31) == 0)
+#ifndef RS_RCP_EXACT
+#define RS_RCP(x) rs_rcp_approx(x)      /* pivot reciprocals of the linear solves: MUFU.RCP (1 ulp) instead of the 12-instruction IEEE sequence on the dependent chain of every pivot */
+#else
 #define RS_RCP(x) __frcp_rn(x)
-#define RS_RSQRT(x) (1.0f / sqrtf(x))      /* fast intrinsics (rsqrtf, __sincosf, __fdividef) were measured: no speed-up, parity loss */
+#endif
+#ifdef RS_RSQRT_EXACT
+#define RS_RSQRT(x) (1.0f / sqrtf(x))
+#else
+#define RS_RSQRT(x) rs_rsqrt_nr(x)      /* MUFU.RSQ + one Newton step (<= 1 ulp) instead of IEEE sqrt followed by IEEE divide (~20 dependent instructions per normalisation) */
+#endif
+#ifdef RS_SINCOS_EXACT
 #define RS_SINCOS(x, s, c) sincosf((x), (s), (c))
+#else
+#define RS_SINCOS(x, s, c) rs_sincos((x), (s), (c))      /* joint angles and half rotation angles, |x| < ~100: two-step reduction + fdlibm kernels, no slow path */
+#endif
+#ifdef RS_DIV_EXACT
 #define RS_DIV(a, b) ((a) / (b))
+#else
+#define RS_DIV(a, b) ((a) * rs_rcp_nr(b))                 /* MUFU.RCP + one Newton step (<= 1 ulp) instead of the IEEE division sequence */
+#endif
 #define RS_UNROLL1 _Pragma("unroll 1")
 #define RS_COLD __device__ __forceinline__
 #define RS_WARP_ANY(p) __any_sync(0xffffffffu, (p))
@@ -91,6 +107,34 @@
 #define RS_WIDTH 0.001f
 
 namespace rs {
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float rs_rsqrt_nr(float x) {
+    float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float e = fmaf(-x * y, y, 1.0f);       // 1 - x y^2
+    return fmaf(0.5f * y, e, y);
+}
+__device__ __forceinline__ float rs_rcp_nr(float x) {
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
+// sin and cos together for moderate arguments (|x| < ~100, where k * pi/2 in two pieces is exact enough): ~30 instructions, <= 1-2 ulp
+__device__ __forceinline__ void rs_sincos(float x, float* sn, float* cs) {
+    const float k = rintf(x * 0.636619772f);
+    float r = fmaf(k, -1.57079637e+0f, x);
+    r = fmaf(k, 4.37113883e-8f, r);
+    const float z = r * r;
+    const float sp = fmaf(z, fmaf(z, fmaf(z, 2.7557314297e-06f, -1.9841270114e-04f), 8.3333337680e-03f), -1.6666667163e-01f);
+    const float sr = fmaf(r * z, sp, r);
+    const float cp = fmaf(z, fmaf(z, fmaf(z, -2.7557314297e-07f, 2.4801587642e-05f), -1.3888889225e-03f), 4.1666667908e-02f);
+    const float cr = fmaf(z * z, cp, fmaf(-0.5f, z, 1.0f));
+    const int q = (int)k & 3;
+    const float s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+    *sn = (q & 2) ? -s0 : s0;
+    *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+__device__ __forceinline__ float rs_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 
 struct V3 { float x, y, z; };
 RS_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -785,8 +829,8 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         s.lsgn[j] = sgn;
         float imp = impedance(pos);
         float diag = isank ? m.iwd_ank[l] : m.iwd_hip[l];
-        float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
-        s.lD[j] = sgn != 0.f ? 1.f / R : 0.f;
+        float R = fmaxf(1e-15f, RS_DIV((1.f - imp) * diag, imp));
+        s.lD[j] = sgn != 0.f ? RS_DIV(1.f, R) : 0.f;
         s.laref[j] = -Kc * imp * pos;           // position term only (see the note on aref below)
     }
     // aref = -B (J v) - K imp pos.  Only its position term is stored: the residual the solver starts from,
@@ -796,9 +840,9 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         float pm = s.cD[k] - RS_MARGIN;
         float imp = impedance(pm);
         float diag = s.caref[k][0] * (1.f + RS_MU * RS_MU);
-        float R = fmaxf(1e-15f, (1.f - imp) * diag / imp);
+        float R = fmaxf(1e-15f, RS_DIV((1.f - imp) * diag, imp));
         R = 2.f * RS_MU * RS_MU * R;
-        s.cD[k] = 1.f / R;
+        s.cD[k] = RS_DIV(1.f, R);
         for (int r = 0; r < 4; r++) s.caref[k][r] = -Kc * imp * pm;
     }
     RS_SYNC();
