@@ -813,9 +813,15 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
     S& s = *c.s;
     const float tc = fmaxf(0.02f, 2.f * c.h);
     const float Kc = 1.f / (RS_DMAX * RS_DMAX * tc * tc);
-    // limits first: sign and D, then J v through rows_of
+    // limits first: sign and D, then J v through rows_of.  The prediction masks (bit j = limit row j, one row per lane) are built with
+    // warp votes on the device -- a lane-per-bit atomicOr on one shared word serialises its 16 lanes
+#if defined(__CUDA_ARCH__)
+    static_assert(S::NU <= 32, "limit masks are one word, one lane per row");
+    bool pv_lane = false, pm_lane = false;
+#else
     if (RS_LANE0) { s.pmask = 0; s.pvalid = 0; }
     RS_SYNC();
+#endif
     RS_LANE_LOOP(j, S::NU) {
         int g = j >> 1, a = c.agent_of_leg(g), l = g - c.leg0(a), isank = j & 1;
         const rs_agent_model& m = c.am[a];
@@ -825,7 +831,11 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         if (qv - lo < 0.f) { sgn = 1.f; pos = qv - lo; } else if (hi - qv < 0.f) { sgn = -1.f; pos = hi - qv; }
         // the row's state at the previous evaluation's solution predicts its state now far better than the sign of the
         // residual at the warm start does (aref moves by B * dvel between RK stages, more than |jar| of a loaded row)
+#if defined(__CUDA_ARCH__)
+        if (sgn != 0.f && s.lsgn[j] == sgn) { pv_lane = true; pm_lane = s.ljar[j] < 0.f; }
+#else
         if (sgn != 0.f && s.lsgn[j] == sgn) { RS_ATOMIC_OR(&s.pvalid, 1 << j); if (s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.pmask, 1 << j); }
+#endif
         s.lsgn[j] = sgn;
         float imp = impedance(pos);
         float diag = isank ? m.iwd_ank[l] : m.iwd_hip[l];
@@ -833,6 +843,9 @@ RS_HD void make_constraints(Ctx<LA, LB>& c) {
         s.lD[j] = sgn != 0.f ? RS_DIV(1.f, R) : 0.f;
         s.laref[j] = -Kc * imp * pos;           // position term only (see the note on aref below)
     }
+#if defined(__CUDA_ARCH__)
+    { const unsigned bv = __ballot_sync(0xffffffffu, pv_lane), bm = __ballot_sync(0xffffffffu, pm_lane); if (RS_LANE0) { s.pvalid = (int)bv; s.pmask = (int)bm; } }
+#endif
     // aref = -B (J v) - K imp pos.  Only its position term is stored: the residual the solver starts from,
     //   jar = J x0 - aref = J (x0 + B v) + K imp pos,
     // takes ONE pass of twists + rows_of over the vector x0 + B v (solve(), first pass) instead of one for J v here and one for J x0 there
@@ -1648,11 +1661,22 @@ RS_HD void solve_first(Ctx<LA, LB>& c) {
         for (int r = 0; r < 4; r++) { s.cjar[k][r] -= s.caref[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
         s.set_cact(k, bits < 16 ? bits : sign);
     }
+#if defined(__CUDA_ARCH__)
+    {   // one vote instead of a zeroing pass, a barrier and per-lane atomics
+        const int j = threadIdx.x & 31, pvd = s.pvalid;
+        bool neg = false;
+        if (j < S::NU) { const float v = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; s.ljar[j] = v; neg = v < 0.f && !((pvd >> j) & 1); }
+        const unsigned b = __ballot_sync(0xffffffffu, neg);
+        if (j == 0) s.lmask = (s.pmask & pvd) | (int)b;
+    }
+    RS_SYNC();
+#else
     RS_LANE_LOOP(j, S::NU) { s.ljar[j] = s.lsgn[j] != 0.f ? s.ljar[j] - s.laref[j] : 1.f; }
     if (RS_LANE0) s.lmask = s.pmask & s.pvalid;
     RS_SYNC();
     RS_LANE_LOOP(j, S::NU) { if (s.ljar[j] < 0.f && !((s.pvalid >> j) & 1)) RS_ATOMIC_OR(&s.lmask, 1 << j); }
     RS_SYNC();
+#endif
 }
 
 // one Newton iteration from the current point (s.x, residuals s.r / s.cjar / s.ljar, active sets); true = converged
@@ -1663,6 +1687,19 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
     RS_ACC(5);
     // coupling that matters for THIS iteration's H: only contacts with active rows contribute J^T D J, so an inter- or
     // intra-agent contact that is inside the margin but not loaded does not force the dense paths
+#if defined(__CUDA_ARCH__)
+    {
+        unsigned cpl = 0;
+        RS_LANE_LOOP(k, s.ncon) {
+            const int bA = s.bA(k), bB = s.bB(k);
+            if (bA >= 0 && s.cact(k) != 0)
+                cpl |= ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1u : 2u;
+        }
+        cpl = __reduce_or_sync(0xffffffffu, cpl);
+        if (RS_LANE0) s.coupled = (int)cpl;
+    }
+    RS_SYNC();
+#else
     if (RS_LANE0) s.coupled = 0;
     RS_SYNC();
     RS_LANE_LOOP(k, s.ncon) {
@@ -1671,6 +1708,7 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
             RS_ATOMIC_OR(&s.coupled, ((bA < 2 ? bA : c.agent_of_leg((bA - 2) % S::LT)) != (bB < 2 ? bB : c.agent_of_leg((bB - 2) % S::LT))) ? 1 : 2);
     }
     RS_SYNC();
+#endif
     if (RS_UNLIKELY(s.coupled == 1)) {      // inter-agent contacts only: list the active ones (fixed order) for the low-rank path
         if (RS_LANE0) {
             int m = 0;
@@ -1732,11 +1770,22 @@ RS_HD bool solve_iter(Ctx<LA, LB>& c) {
         for (int r = 0; r < 4; r++) { s.cjar[k][r] += alpha * s.cjd[k][r]; if (s.cjar[k][r] < 0.f) sign |= 1 << r; }
         s.set_cact(k, sign);             // sign set at the new point
     }
+#if defined(__CUDA_ARCH__)
+    {
+        const int j = threadIdx.x & 31;
+        bool neg = false;
+        if (j < S::NU && s.lsgn[j] != 0.f) { const float v = s.ljar[j] + alpha * s.ljd[j]; s.ljar[j] = v; neg = v < 0.f; }
+        const unsigned b = __ballot_sync(0xffffffffu, neg);
+        if (j == 0) s.lmask = (int)b;                                                                      // sign set at the new point
+    }
+    RS_SYNC();
+#else
     RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f) s.ljar[j] += alpha * s.ljd[j]; }
     if (RS_LANE0) s.lmask = 0;
     RS_SYNC();
     RS_LANE_LOOP(j, S::NU) { if (s.lsgn[j] != 0.f && s.ljar[j] < 0.f) RS_ATOMIC_OR(&s.lmask, 1 << j); }     // sign set at the new point
     RS_SYNC();
+#endif
     RS_ACC(4);
     return same != 0;
 }
