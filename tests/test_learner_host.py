@@ -156,6 +156,34 @@ def test_legacy_shuffle_replay_is_bit_exact():
         assert (tail_ref[0] == tail[0]).all() and (tail_ref[1] == tail[1]).all()
 
 
+def test_int32_shuffle_and_pipelined_cut_are_the_same_schedule():
+    """EpochPermutations shuffles an int32 working array (rs_legacy_shuffle32) and, data-parallel, cuts each permutation on a second
+    helper thread: the permutations must still be np.random.shuffle's, the generator must end where NumPy's would, and the cut must
+    equal the masks of the un-cut permutation for every rank."""
+    from robosumo_selfplay_b200.dist import EpochPermutations, split_minibatch
+    n, nep, nbt, world = 30011, 3, 4096, 3
+    np.random.seed(11)
+    a = np.arange(n); ref = []
+    for _ in range(nep):
+        np.random.shuffle(a); ref.append(a.copy())
+    tail_ref = np.random.randint(0, 1 << 30, 4)
+    np.random.seed(11)
+    got = list(EpochPermutations(n, nep, ahead=nep, dtype=np.int32))
+    assert (np.random.randint(0, 1 << 30, 4) == tail_ref).all()
+    for r, g in zip(ref, got):
+        assert g.dtype == np.int32 and (r == g).all()
+    bounds = [0, 9000, 20000, n]
+    for rank in range(world):
+        lo, hi = bounds[rank], bounds[rank + 1]
+        np.random.seed(11)
+        cuts = list(EpochPermutations(n, nep, ahead=1, dtype=np.int32, split=(nbt, lo, hi)))
+        assert (np.random.randint(0, 1 << 30, 4) == tail_ref).all()
+        for r, sp in zip(ref, cuts):
+            for m in range((n + nbt - 1) // nbt):
+                want = split_minibatch(r[m * nbt:(m + 1) * nbt], lo, hi)
+                assert sp.counts[m] == len(want) and (sp.idx[m, :sp.counts[m]] == want).all()
+
+
 def test_epoch_permutations_commit_only_what_is_consumed():
     """EpochPermutations hands out the same permutations as successive np.random.shuffle calls and leaves the global stream
     where the reference would be, also when the epochs stop early."""
