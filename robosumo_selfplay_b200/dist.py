@@ -72,16 +72,22 @@ class Comm:
         from . import _lib
         L = _lib.lib()
         h = ctypes.c_void_p()
-        _lib.check(L.rs_peer_create(self.rank, self.world, int(nfloats), int(device_index), ctypes.byref(h)))
         nb = L.rs_peer_handle_bytes()
         mine = (ctypes.c_ubyte * nb)()
-        _lib.check(L.rs_peer_export(h, mine))
         dev = t.device('cuda', device_index)
+        ok = L.rs_peer_create(self.rank, self.world, int(nfloats), int(device_index), ctypes.byref(h)) == 0 and L.rs_peer_export(h, mine) == 0
         gathered = t.empty(self.world * nb, dtype=t.uint8, device=dev)
         self.dist.all_gather_into_tensor(gathered, t.tensor(list(mine), dtype=t.uint8, device=dev))
-        table = gathered.cpu().numpy().tobytes()
-        _lib.check(L.rs_peer_connect(h, table))
-        self.barrier()                                    # nobody signals a peer that has not mapped the buffers yet
+        if ok:
+            ok = L.rs_peer_connect(h, gathered.cpu().numpy().tobytes()) == 0
+        # all or nothing: a rank that cannot map a peer (no P2P path between two GPUs, IPC disabled in a container) sends everybody
+        # back to the NCCL all-reduce; this all-reduce is also the barrier after which peers may signal each other
+        agree = t.tensor([1 if ok else 0], dtype=t.int32, device=dev)
+        self.dist.all_reduce(agree, op=self.dist.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            if h:
+                L.rs_peer_destroy(h)
+            return None
         return h
 
     def shard(self, n_global):
