@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(32 * RS_WPB) k_step(EnvDev d, const float* __r
     Ctx<LA, LB> c;
     warp_setup(c, d, sm_am, smem_raw);
     float before[4];
-    if constexpr (RS_TRIP_MACHINE && LA + LB <= 8) {
+    if constexpr (RS_TRIP_MACHINE && LA + LB <= RS_TRIP_MAX_LEGS) {
         if (blockIdx.x == 0 && threadIdx.x == 0) d.next[d.tick ^ 1] = 0;
         int e = -1;
         simulate_trips(c, d.P.frame_skip, [&](bool finish) -> bool {
@@ -480,7 +480,7 @@ int rs_step(rs_env* h, const float* actions, float* obs, float* rew, uint8_t* do
     if (!h || !actions || !obs || !rew || !done) return fail(RS_ERR_ARG, "rs_step: bad argument%s", "");
     return dispatch(h, [&](auto la, auto lb) {
         constexpr int A = decltype(la)::value, B = decltype(lb)::value;
-        if (RS_TRIP_MACHINE && A + B <= 8) {      // persistent blocks, pairs handed out by a device counter
+        if (RS_TRIP_MACHINE && A + B <= RS_TRIP_MAX_LEGS) {      // persistent blocks, pairs handed out by a device counter
             int grid = (h->d.E + h->wpb - 1) / h->wpb;
             h->d.persistent = grid > h->sms ? 1 : 0;
             if (grid > h->sms) grid = h->sms;

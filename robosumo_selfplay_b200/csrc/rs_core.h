@@ -1913,6 +1913,9 @@ RS_HD void substep_begin(Ctx<LA, LB>& c) {
 #define RS_TRIP_ANY(p) (p)      // device: __syncthreads_or -- the block-wide vote doubles as the barrier that re-aligns the warps
 #define RS_TRIP_SYNC()
 #endif
+#ifndef RS_TRIP_MAX_LEGS
+#define RS_TRIP_MAX_LEGS 12     // pairs with at most this many legs (Ant and Bug pairs, Ant-Spider) re-align per trip and run persistent blocks; the larger ones per evaluation (Bug-Bug 3.91 -> 3.65 ms, Spider-Spider equal)
+#endif
 #ifndef RS_TRIP_MACHINE
 #define RS_TRIP_MACHINE 1      // 0: re-align per evaluation for every morphology (round-1 behaviour)
 #endif
@@ -1956,7 +1959,7 @@ RS_HD void simulate(Ctx<LA, LB>& c, int nsub) {
     // measured at E = 4096 (tools/bench_morphologies.py): Ant 1.65 -> 1.61 ms per trip, Bug 5.01 -> 5.06 (equal), Spider 7.56 -> 8.11:
     // the larger bodies have 19 / 15 warps per block (bigger slabs) and less to gain from not waiting, so they keep the
     // per-evaluation re-alignment
-    if constexpr (RS_TRIP_MACHINE && LA + LB <= 8) {
+    if constexpr (RS_TRIP_MACHINE && LA + LB <= RS_TRIP_MAX_LEGS) {
         bool first = true;
         simulate_trips(c, nsub, [&](bool) -> bool { const bool r = first; first = false; return r; });       // the one pair already in the slab
     } else {
